@@ -1,0 +1,174 @@
+/* rsfusion.h -- C ABI of the B200-native voxel-hashing TSDF + semantic fusion engine.
+ *
+ * This is the drop-in boundary for RA-SLAM's `TSDFGrid` (reference utils/tsdf/voxel_tsdf.cuh:39-145)
+ * and the table/pool below it (`VoxelHashTable` utils/tsdf/voxel_hash.cuh:47-166, `VoxelMemPool`
+ * utils/tsdf/voxel_mem.cuh:97-176).  Plain pointers and sizes only: no OpenCV / Eigen / GL / torch
+ * types cross this line.  The header-only C++ adapter include/rsfusion/tsdf_grid.hpp puts the
+ * reference's class and method names back on top of it.
+ *
+ * Conventions
+ *   - every entry point returns an `int` status (RSF_OK == 0); no exceptions cross the ABI;
+ *     rsf_last_error() gives a human-readable message for the calling thread's last failure.
+ *   - images are row-major, tightly packed (`cv::Mat::isContinuous()`), H rows x W columns.
+ *   - K  = {fx, fy, cx, cy}                       (CameraIntrinsics<float>, utils/cuda/camera.cuh:13-31)
+ *   - pose = {qw, qx, qy, qz, tx, ty, tz} of cam_T_world (SE3<float>: Eigen quaternion + translation,
+ *     utils/cuda/lie_group.cuh:8-45).  The quaternion is used as given (not re-normalised).
+ *   - `*_device` variants take device pointers valid on the grid's device and only enqueue work on
+ *     the grid's stream; the host variants are blocking, like the reference's methods
+ *     (voxel_tsdf.cu:450, :901).
+ *   - a grid is not re-entrant (the reference serialises calls with TSDFSystem::mtx_read_,
+ *     modules/tsdf_module.cc:40-107); different grids may be used from different threads.
+ *   - there is no CPU fallback: every call fails with RSF_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RSFUSION_H_
+#define RSFUSION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RSF_API __attribute__((visibility("default")))
+#else
+#define RSF_API
+#endif
+
+enum rsf_status {
+  RSF_OK = 0,
+  RSF_ERR_INVALID = 1,      /* bad argument (NULL pointer, size, dtype contract)            */
+  RSF_ERR_CUDA = 2,         /* CUDA runtime error, message in rsf_last_error()             */
+  RSF_ERR_POOL_FULL = 3,    /* voxel-block pool exhausted (reference: device assert,       */
+                            /* utils/tsdf/voxel_mem.cu:38-39)                              */
+  RSF_ERR_TABLE_FULL = 4,   /* hash table probe limit reached                              */
+  RSF_ERR_CAPACITY = 5      /* caller-provided output buffer too small (size is returned)  */
+};
+
+typedef struct rsf_grid_s* rsf_grid_t;
+
+/* Construction parameters.  voxel_size/truncation are the two arguments of
+ * TSDFGrid::TSDFGrid (voxel_tsdf.cu:376-377); the rest replace compile-time #defines of the
+ * reference (NUM_BLOCK voxel_mem.cuh:11-13, NUM_ENTRY voxel_hash.cuh:13-25, MAX_IMG_SIZE
+ * voxel_tsdf.cu:11-13) and add the spatial-shard description (new).  Zero selects the default. */
+typedef struct rsf_options {
+  float voxel_size;        /* [m]                                                           */
+  float truncation;        /* [m]                                                           */
+  int device;              /* CUDA ordinal; -1 = current device                             */
+  int pool_blocks;         /* capacity in 8^3-voxel blocks; default 1<<18 (reference)       */
+  int table_slots_log2;    /* open-addressed slots; default 22 (reference NUM_ENTRY)        */
+  int max_pixels;          /* largest H*W accepted; default 1920*1080 (reference)           */
+  int shard_rank;          /* spatial sharding: this grid integrates only blocks it owns    */
+  int shard_world;         /*   (+halo); world <= 1 disables sharding                       */
+  int shard_shift;         /*   owner = mix(block_pos >> shift) % world; default 1          */
+  int shard_halo;          /*   redundant halo in blocks; default 1                         */
+  void* stream;            /* optional external cudaStream_t; NULL = library-owned stream   */
+  unsigned flags;          /* reserved, must be 0                                           */
+} rsf_options;
+
+/* Per-frame counters of the last rsf_integrate* call (reference logs only block counts,
+ * voxel_tsdf.cu:442,451,865). */
+typedef struct rsf_frame_stats {
+  int64_t active_blocks;   /* == TSDFGrid's hash_table_.NumActiveBlock() after the call     */
+  int64_t new_blocks;      /* blocks allocated by this frame                                */
+  int64_t visible_blocks;  /* blocks selected for integration                               */
+  int64_t updated_voxels;  /* voxels that passed sdf > -truncation                          */
+  int64_t carved_blocks;   /* blocks removed by space carving                               */
+  int64_t high_water;      /* pool slots ever used                                          */
+} rsf_frame_stats;
+
+RSF_API void rsf_default_options(rsf_options* opts);
+RSF_API int rsf_abi_version(void);
+RSF_API const char* rsf_last_error(void);
+
+/* TSDFGrid::TSDFGrid / ~TSDFGrid (voxel_tsdf.cu:376-414). */
+RSF_API int rsf_create(const rsf_options* opts, rsf_grid_t* out);
+RSF_API int rsf_destroy(rsf_grid_t g);
+
+/* TSDFGrid::Integrate (voxel_tsdf.cu:416-452): allocate -> select visible -> integrate -> carve.
+ * rgb: H*W*3 u8 (RGB order, CV_8UC3); depth: H*W f32 metres, z-depth, 0 = invalid (CV_32FC1);
+ * ht/lt: H*W f32 high-/low-touch probabilities (CV_32FC1).  Host buffers; blocking. */
+RSF_API int rsf_integrate(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
+                  int H, int W, float max_depth, const float K[4], const float pose[7]);
+/* Same with the frame already resident in device memory; asynchronous on the grid's stream. */
+RSF_API int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht,
+                         const float* lt, int H, int W, float max_depth, const float K[4],
+                         const float pose[7]);
+
+/* TSDFGrid::RayCast (voxel_tsdf.cu:885-902).  rgba / normal are the reference's two RGBA8 images
+ * (img_tsdf_rgba_, img_tsdf_normal_); depth (z of the refined hit in the camera frame, 0 = no hit)
+ * and prob (fused probability at the hit voxel) are new outputs.  Any output may be NULL.
+ * Host buffers; blocking. */
+RSF_API int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
+                uint8_t* rgba, uint8_t* normal, float* depth, float* prob);
+/* Device outputs; asynchronous on the grid's stream. */
+RSF_API int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
+                       uint8_t* rgba, uint8_t* normal, float* depth, float* prob);
+
+/* Block until everything enqueued on the grid's stream is done; surfaces device-side errors
+ * (pool/table exhaustion) of the asynchronous variants. */
+RSF_API int rsf_synchronize(rsf_grid_t g);
+
+/* VoxelHashTable::NumActiveBlock (voxel_hash.cu:225). */
+RSF_API int rsf_num_active_blocks(rsf_grid_t g, int64_t* n);
+RSF_API int rsf_get_stats(rsf_grid_t g, rsf_frame_stats* stats);
+
+/* TSDFGrid::GatherValid (voxel_tsdf.cu:476-502): rows of VoxelSpatialTSDF {x,y,z,tsdf} (16 B);
+ * TSDFGrid::GatherValidSemantic (:504-530): rows of VoxelSpatialTSDFSEGM {x,y,z,tsdf,prob} (20 B);
+ * TSDFGrid::GatherVoxels (:532-559): GatherValid restricted to blocks fully inside
+ * bounds = {xmin,xmax,ymin,ymax,zmin,zmax} [m] (BoundingCube<float>, voxel_tsdf.cuh:20-34).
+ * Size-query-then-fill: call with rows == NULL to get *n_rows; with rows != NULL, cap_rows must be
+ * >= the number of rows or RSF_ERR_CAPACITY is returned (and *n_rows still set).  With sharding,
+ * only rows of blocks this rank owns are produced (halo copies are dropped). */
+RSF_API int rsf_gather_valid(rsf_grid_t g, float* rows, int64_t cap_rows, int64_t* n_rows);
+RSF_API int rsf_gather_valid_semantic(rsf_grid_t g, float* rows, int64_t cap_rows, int64_t* n_rows);
+RSF_API int rsf_gather_voxels(rsf_grid_t g, const float bounds[6], float* rows, int64_t cap_rows, int64_t* n_rows);
+
+/* TSDFGrid::GatherValidMesh (voxel_tsdf.cu:736-845): marching cubes over all active blocks.
+ * vertices: n_vertices x 3 f32 [m]; triangles: n_triangles x 3 i32 indices into vertices;
+ * vertex_prob: n_vertices f32.  Same size-query-then-fill convention (pass NULL buffers first). */
+RSF_API int rsf_gather_valid_mesh(rsf_grid_t g, float* vertices, int64_t cap_vertices, int64_t* n_vertices,
+                          int32_t* triangles, int64_t cap_triangles, int64_t* n_triangles,
+                          float* vertex_prob);
+
+/* Raw block state for parity tests: coords n x 3 i16 (block coordinates), tsdf n x 512 f32,
+ * rgbw n x 512 x 4 u8 (r,g,b,weight), prob n x 512 f32; voxel order x + 8y + 64z
+ * (OffsetToIndex, voxel_mem.cuh:67-70).  Block order is unspecified.  Outputs may be NULL. */
+RSF_API int rsf_export_blocks(rsf_grid_t g, int owned_only, int16_t* coords, float* tsdf, uint8_t* rgbw,
+                      float* prob, int64_t cap_blocks, int64_t* n_blocks);
+
+/* ---- table / pool level operations (the reference exercises these from its unit tests,
+ * utils/tests/voxel_hash_test.cu:36-54, through 1-block kernels) ----------------------------- */
+
+/* Hash (voxel_hash.cu:19-23); mask = NUM_BUCKET-1 = 2097151 in the reference. */
+RSF_API uint32_t rsf_hash(int16_t x, int16_t y, int16_t z, uint32_t mask);
+/* Owner rank of a block under spatial sharding (new). */
+RSF_API uint32_t rsf_shard_owner(int16_t x, int16_t y, int16_t z, int shift, int world);
+/* VoxelHashTable::Allocate for n block coordinates (n x 3 i16, host), one launch. */
+RSF_API int rsf_allocate_blocks(rsf_grid_t g, const int16_t* block_coords, int n);
+/* VoxelHashTable::Delete for n block coordinates. */
+RSF_API int rsf_delete_blocks(rsf_grid_t g, const int16_t* block_coords, int n);
+/* VoxelHashTable::Retrieve<VoxelTSDF|VoxelRGBW|VoxelSEGM> at n voxel coordinates (n x 3 i16).
+ * found[i] = 1 if the voxel's block is allocated, else 0 and the reference's miss defaults are
+ * returned (tsdf -10, rgbw 0, prob 0; voxel_types.cu:3,8,11).  Outputs may be NULL. */
+RSF_API int rsf_retrieve_voxels(rsf_grid_t g, const int16_t* voxel_coords, int n, float* tsdf, uint8_t* rgbw,
+                        float* prob, uint8_t* found);
+/* *RetrieveMutable<...>(p) = value at n voxel coordinates; fields may be NULL (left untouched).
+ * written[i] = 0 when the voxel's block is not allocated. */
+RSF_API int rsf_assign_voxels(rsf_grid_t g, const int16_t* voxel_coords, int n, const float* tsdf,
+                      const uint8_t* rgbw, const float* prob, uint8_t* written);
+/* VoxelHashTable::RetrieveTSDF (voxel_hash.cu:161-188) at n continuous grid points (n x 3 f32). */
+RSF_API int rsf_retrieve_tsdf_trilinear(rsf_grid_t g, const float* points, int n, float* tsdf);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so callers can hand rsf_integrate /
+ * rsf_raycast page-locked buffers and get true asynchronous DMA. */
+RSF_API int rsf_host_alloc(void** ptr, size_t bytes);
+RSF_API int rsf_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSFUSION_H_ */

@@ -1,0 +1,538 @@
+// rsf_api.cu -- host side of the C ABI declared in include/rsfusion.h.
+//
+// Orchestration that replaces TSDFGrid's host methods (utils/tsdf/voxel_tsdf.cu:376-559,
+// :736-902).  Per Integrate the reference issues ~10 launches, 4 pageable H2D copies on two
+// streams, 4 host synchronisations and 2 synchronous D2H counter reads; here a
+// frame is 4 H2D copies + 1 memset + 3 launches on one stream and, for the blocking host entry
+// point, one 128-byte counter read-back and one synchronisation.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "rsf_kernels.h"
+#include "rsfusion.h"
+
+using namespace rsf;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define RSF_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(RSF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+struct rsf_grid_s {
+  rsf_options opt{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  GridView view{};
+  size_t table_slots = 0;
+  size_t max_pixels = 0;
+  // frame staging (device)
+  uint8_t* d_rgb = nullptr;
+  float *d_depth = nullptr, *d_ht = nullptr, *d_lt = nullptr;
+  float4* d_frame = nullptr;
+  // raycast outputs (device)
+  uchar4 *d_rgba = nullptr, *d_normal = nullptr;
+  float *d_rdepth = nullptr, *d_rprob = nullptr;
+  // pinned mirror of the device counters
+  Counters* h_ctr = nullptr;
+  rsf_frame_stats last{};
+};
+
+namespace {
+
+int check_grid(rsf_grid_t g) {
+  if (!g) return fail(RSF_ERR_INVALID, "null grid handle");
+  return RSF_OK;
+}
+
+int make_frame(rsf_grid_t g, int H, int W, float max_depth, const float* K, const float* pose, Frame* f) {
+  if (!K || !pose) return fail(RSF_ERR_INVALID, "K / pose must not be NULL");
+  if (H <= 0 || W <= 0 || (size_t)H * (size_t)W > g->max_pixels)
+    return fail(RSF_ERR_INVALID, "image %dx%d outside (0, max_pixels=%zu]", W, H, g->max_pixels);
+  f->K = Intr{K[0], K[1], K[2], K[3]};
+  f->Ki = f->K.inverse();                       // CameraParams ctor, camera.cuh:61-67
+  f->T_cw = Pose{Quat{pose[0], pose[1], pose[2], pose[3]}, V3{pose[4], pose[5], pose[6]}};
+  f->T_wc = f->T_cw.inverse();                  // cam_T_world.Inverse() on the host, voxel_tsdf.cu:459,892
+  f->W = W;
+  f->H = H;
+  f->vs = g->opt.voxel_size;
+  f->tr = g->opt.truncation;
+  f->max_depth = max_depth;
+  return RSF_OK;
+}
+
+// read the counters back (blocking) and translate sticky device errors
+int sync_counters(rsf_grid_t g) {
+  RSF_CUDA(cudaMemcpyAsync(g->h_ctr, g->view.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  const Counters& c = *g->h_ctr;
+  g->last.active_blocks = (int64_t)g->view.pool_blocks - c.free_count;
+  g->last.high_water = c.high_water;
+  g->last.new_blocks = (int64_t)c.new_blocks;
+  g->last.visible_blocks = c.vis_count;
+  g->last.updated_voxels = (int64_t)c.updated_voxels;
+  g->last.carved_blocks = (int64_t)c.carved_blocks;
+  if (c.error) {
+    const unsigned e = c.error;
+    cudaMemsetAsync(&g->view.ctr->error, 0, sizeof(unsigned), g->stream);
+    if (e & kErrPoolFull)
+      return fail(RSF_ERR_POOL_FULL, "voxel-block pool exhausted (%d blocks); raise rsf_options.pool_blocks",
+                  g->view.pool_blocks);
+    if (e & kErrTableFull) return fail(RSF_ERR_TABLE_FULL, "hash table full (%zu slots)", g->table_slots);
+  }
+  return RSF_OK;
+}
+
+int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
+                      const float* lt) {
+  RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrFrameOff, 0, kCtrFrameBytes, g->stream));
+  launch_allocate(g->view, f, rgb, depth, ht, lt, g->d_frame, g->stream);
+  launch_select_visible(g->view, f, g->sm_count, g->stream);
+  launch_integrate(g->view, f, g->d_frame, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+int gather_rows(rsf_grid_t g, int mode, const float* bounds, int ncol, float* rows, int64_t cap_rows, int64_t* n_rows) {
+  if (int rc = check_grid(g)) return rc;
+  if (!n_rows) return fail(RSF_ERR_INVALID, "n_rows must not be NULL");
+  DeviceGuard dg(g->device);
+  S3 lo{0, 0, 0}, hi{0, 0, 0};
+  if (mode == 1) {
+    if (!bounds) return fail(RSF_ERR_INVALID, "bounds must not be NULL");
+    // BoundingCube<float>::Scale<short>(1./voxel_size), voxel_tsdf.cuh:28-33, voxel_tsdf.cu:534
+    const float s = (float)(1. / g->opt.voxel_size);
+    lo = S3{(short)(bounds[0] * s), (short)(bounds[2] * s), (short)(bounds[4] * s)};
+    hi = S3{(short)(bounds[1] * s), (short)(bounds[3] * s), (short)(bounds[5] * s)};
+  }
+  RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
+  launch_gather_select(g->view, mode, g->opt.shard_world > 1, lo, hi, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (int rc = sync_counters(g)) return rc;
+  const int nblk = g->h_ctr->gather_count;
+  *n_rows = (int64_t)nblk * kBlockVol;
+  if (!rows) return RSF_OK;
+  if (cap_rows < *n_rows) return fail(RSF_ERR_CAPACITY, "need %lld rows, capacity %lld", (long long)*n_rows, (long long)cap_rows);
+  if (nblk == 0) return RSF_OK;
+  float* d_rows = nullptr;
+  const size_t bytes = (size_t)*n_rows * ncol * sizeof(float);
+  RSF_CUDA(cudaMallocAsync(&d_rows, bytes, g->stream));
+  launch_download_rows(g->view, g->opt.voxel_size, nblk, ncol, d_rows, g->sm_count, g->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rows, d_rows, bytes, cudaMemcpyDeviceToHost, g->stream);
+  cudaFreeAsync(d_rows, g->stream);
+  if (e != cudaSuccess) return fail(RSF_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaStream_t s;
+  explicit DevBuf(cudaStream_t st) : s(st) {}
+  cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), s); }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void rsf_default_options(rsf_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof *o);
+  o->voxel_size = 0.01f;
+  o->truncation = 0.06f;
+  o->device = -1;
+  o->pool_blocks = 1 << 18;          // NUM_BLOCK, voxel_mem.cuh:11-13
+  o->table_slots_log2 = 22;          // NUM_ENTRY, voxel_hash.cuh:13-25
+  o->max_pixels = 1920 * 1080;       // MAX_IMG_SIZE, voxel_tsdf.cu:11-13
+  o->shard_rank = 0;
+  o->shard_world = 1;
+  o->shard_shift = 1;
+  o->shard_halo = 1;
+}
+
+int rsf_abi_version(void) { return RSF_ABI_VERSION; }
+const char* rsf_last_error(void) { return g_last_error.c_str(); }
+
+int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
+  if (!opts || !out) return fail(RSF_ERR_INVALID, "opts / out must not be NULL");
+  *out = nullptr;
+  rsf_options o = *opts;
+  rsf_options d;
+  rsf_default_options(&d);
+  if (o.pool_blocks <= 0) o.pool_blocks = d.pool_blocks;
+  if (o.table_slots_log2 <= 0) o.table_slots_log2 = d.table_slots_log2;
+  if (o.max_pixels <= 0) o.max_pixels = d.max_pixels;
+  if (o.shard_world <= 0) o.shard_world = 1;
+  if (o.shard_shift < 0) o.shard_shift = d.shard_shift;
+  if (o.shard_halo < 0) o.shard_halo = d.shard_halo;
+  if (!(o.voxel_size > 0.f) || !(o.truncation > 0.f)) return fail(RSF_ERR_INVALID, "voxel_size and truncation must be > 0");
+  if (o.table_slots_log2 > 30 || ((size_t)1 << o.table_slots_log2) < 2 * (size_t)o.pool_blocks)
+    return fail(RSF_ERR_INVALID, "table_slots_log2=%d must give >= 2x pool_blocks=%d slots", o.table_slots_log2, o.pool_blocks);
+  if (o.shard_rank < 0 || o.shard_rank >= o.shard_world) return fail(RSF_ERR_INVALID, "shard_rank outside [0, shard_world)");
+  if (o.flags != 0) return fail(RSF_ERR_INVALID, "flags must be 0");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(RSF_ERR_CUDA, "no CUDA device (%s): rsfusion has no CPU fallback", cudaGetErrorString(e));
+  int dev = o.device;
+  if (dev < 0) RSF_CUDA(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(RSF_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
+  cudaDeviceProp prop;
+  RSF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(RSF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+
+  DeviceGuard dg(dev);
+  rsf_grid_s* g = new (std::nothrow) rsf_grid_s;
+  if (!g) return fail(RSF_ERR_INVALID, "out of host memory");
+  g->opt = o;
+  g->device = dev;
+  g->sm_count = prop.multiProcessorCount;
+  g->table_slots = (size_t)1 << o.table_slots_log2;
+  g->max_pixels = (size_t)o.max_pixels;
+  if (o.stream) {
+    g->stream = (cudaStream_t)o.stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete g;
+      return fail(RSF_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    g->own_stream = true;
+  }
+  GridView& v = g->view;
+  v.slot_mask = (uint32_t)(g->table_slots - 1);
+  v.pool_blocks = o.pool_blocks;
+  v.shard = ShardSpec{o.shard_rank, o.shard_world, o.shard_shift, o.shard_halo};
+  const size_t P = g->max_pixels;
+  bool ok = true;
+  auto A = [&](void** p, size_t bytes) { ok = ok && cudaMalloc(p, bytes) == cudaSuccess; };
+  A((void**)&v.keys, g->table_slots * sizeof(uint64_t));
+  A((void**)&v.vals, g->table_slots * sizeof(int));
+  A((void**)&v.pool, (size_t)o.pool_blocks * kSlabBytes);
+  A((void**)&v.meta, (size_t)o.pool_blocks * sizeof(BlockMeta));
+  A((void**)&v.heap, (size_t)o.pool_blocks * sizeof(int));
+  A((void**)&v.vis_list, (size_t)o.pool_blocks * sizeof(int));
+  A((void**)&v.gather_list, (size_t)o.pool_blocks * sizeof(int));
+  A((void**)&v.ctr, sizeof(Counters));
+  A((void**)&g->d_rgb, P * 3);
+  A((void**)&g->d_depth, P * sizeof(float));
+  A((void**)&g->d_ht, P * sizeof(float));
+  A((void**)&g->d_lt, P * sizeof(float));
+  A((void**)&g->d_frame, P * sizeof(float4));
+  A((void**)&g->d_rgba, P * sizeof(uchar4));
+  A((void**)&g->d_normal, P * sizeof(uchar4));
+  A((void**)&g->d_rdepth, P * sizeof(float));
+  A((void**)&g->d_rprob, P * sizeof(float));
+  ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
+  if (ok) {
+    ok = ok && cudaMemsetAsync(v.keys, 0xff, g->table_slots * sizeof(uint64_t), g->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(v.vals, 0xff, g->table_slots * sizeof(int), g->stream) == cudaSuccess;
+    launch_init_pool(v, g->stream);
+    ok = ok && cudaStreamSynchronize(g->stream) == cudaSuccess;
+  }
+  if (!ok) {
+    const cudaError_t le = cudaGetLastError();
+    rsf_destroy(g);
+    return fail(RSF_ERR_CUDA, "device allocation / initialisation failed: %s", cudaGetErrorString(le));
+  }
+  *out = g;
+  return RSF_OK;
+}
+
+int rsf_destroy(rsf_grid_t g) {
+  if (!g) return RSF_OK;
+  DeviceGuard dg(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  GridView& v = g->view;
+  void* ptrs[] = {v.keys,   v.vals,     v.pool,     v.meta,    v.heap,    v.vis_list, v.gather_list, v.ctr,     g->d_rgb,
+                  g->d_depth, g->d_ht,  g->d_lt,    g->d_frame, g->d_rgba, g->d_normal, g->d_rdepth,  g->d_rprob};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (g->h_ctr) cudaFreeHost(g->h_ctr);
+  if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  return RSF_OK;
+}
+
+int rsf_integrate(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H, int W,
+                  float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!rgb || !depth || !ht || !lt) return fail(RSF_ERR_INVALID, "rgb / depth / ht / lt must not be NULL");
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  const size_t P = (size_t)H * W;
+  RSF_CUDA(cudaMemcpyAsync(g->d_depth, depth, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(g->d_rgb, rgb, P * 3, cudaMemcpyHostToDevice, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(g->d_ht, ht, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(g->d_lt, lt, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  if (int rc = enqueue_integrate(g, f, g->d_rgb, g->d_depth, g->d_ht, g->d_lt)) return rc;
+  return sync_counters(g);
+}
+
+int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H,
+                         int W, float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!rgb || !depth || !ht || !lt) return fail(RSF_ERR_INVALID, "rgb / depth / ht / lt must not be NULL");
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  return enqueue_integrate(g, f, rgb, depth, ht, lt);
+}
+
+int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,
+                       uint8_t* normal, float* depth, float* prob) {
+  if (int rc = check_grid(g)) return rc;
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  // step_size = truncation / 2, voxel_tsdf.cu:892
+  launch_raycast(g->view, f, g->opt.truncation / 2, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
+                 depth, prob, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,
+                uint8_t* normal, float* depth, float* prob) {
+  if (int rc = check_grid(g)) return rc;
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  launch_raycast(g->view, f, g->opt.truncation / 2, rgba ? g->d_rgba : nullptr, normal ? g->d_normal : nullptr,
+                 depth ? g->d_rdepth : nullptr, prob ? g->d_rprob : nullptr, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  const size_t P = (size_t)H * W;
+  if (rgba) RSF_CUDA(cudaMemcpyAsync(rgba, g->d_rgba, P * 4, cudaMemcpyDeviceToHost, g->stream));
+  if (normal) RSF_CUDA(cudaMemcpyAsync(normal, g->d_normal, P * 4, cudaMemcpyDeviceToHost, g->stream));
+  if (depth) RSF_CUDA(cudaMemcpyAsync(depth, g->d_rdepth, P * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  if (prob) RSF_CUDA(cudaMemcpyAsync(prob, g->d_rprob, P * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+int rsf_synchronize(rsf_grid_t g) {
+  if (int rc = check_grid(g)) return rc;
+  DeviceGuard dg(g->device);
+  return sync_counters(g);
+}
+
+int rsf_num_active_blocks(rsf_grid_t g, int64_t* n) {
+  if (int rc = check_grid(g)) return rc;
+  if (!n) return fail(RSF_ERR_INVALID, "n must not be NULL");
+  DeviceGuard dg(g->device);
+  if (int rc = sync_counters(g)) return rc;
+  *n = g->last.active_blocks;
+  return RSF_OK;
+}
+
+int rsf_get_stats(rsf_grid_t g, rsf_frame_stats* s) {
+  if (int rc = check_grid(g)) return rc;
+  if (!s) return fail(RSF_ERR_INVALID, "stats must not be NULL");
+  DeviceGuard dg(g->device);
+  if (int rc = sync_counters(g)) return rc;
+  *s = g->last;
+  return RSF_OK;
+}
+
+int rsf_gather_valid(rsf_grid_t g, float* rows, int64_t cap_rows, int64_t* n_rows) {
+  return gather_rows(g, 0, nullptr, 4, rows, cap_rows, n_rows);
+}
+int rsf_gather_valid_semantic(rsf_grid_t g, float* rows, int64_t cap_rows, int64_t* n_rows) {
+  return gather_rows(g, 0, nullptr, 5, rows, cap_rows, n_rows);
+}
+int rsf_gather_voxels(rsf_grid_t g, const float bounds[6], float* rows, int64_t cap_rows, int64_t* n_rows) {
+  return gather_rows(g, 1, bounds, 4, rows, cap_rows, n_rows);
+}
+
+int rsf_gather_valid_mesh(rsf_grid_t g, float*, int64_t, int64_t*, int32_t*, int64_t, int64_t*, float*) {
+  if (int rc = check_grid(g)) return rc;
+  return fail(RSF_ERR_INVALID, "rsf_gather_valid_mesh: marching cubes not implemented yet");
+}
+
+int rsf_export_blocks(rsf_grid_t g, int owned_only, int16_t* coords, float* tsdf, uint8_t* rgbw, float* prob,
+                      int64_t cap_blocks, int64_t* n_blocks) {
+  if (int rc = check_grid(g)) return rc;
+  if (!n_blocks) return fail(RSF_ERR_INVALID, "n_blocks must not be NULL");
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
+  launch_gather_select(g->view, 0, owned_only, S3{0, 0, 0}, S3{0, 0, 0}, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (int rc = sync_counters(g)) return rc;
+  const int nblk = g->h_ctr->gather_count;
+  *n_blocks = nblk;
+  if (!coords && !tsdf && !rgbw && !prob) return RSF_OK;
+  if (cap_blocks < nblk) return fail(RSF_ERR_CAPACITY, "need %d blocks, capacity %lld", nblk, (long long)cap_blocks);
+  if (nblk == 0) return RSF_OK;
+  DevBuf<short> dc(g->stream);
+  DevBuf<float> dt(g->stream), dp(g->stream);
+  DevBuf<uint32_t> dr(g->stream);
+  const size_t nv = (size_t)nblk * kBlockVol;
+  if (coords) RSF_CUDA(dc.alloc((size_t)nblk * 3));
+  if (tsdf) RSF_CUDA(dt.alloc(nv));
+  if (rgbw) RSF_CUDA(dr.alloc(nv));
+  if (prob) RSF_CUDA(dp.alloc(nv));
+  launch_export_blocks(g->view, nblk, dc.p, dt.p, dr.p, dp.p, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (coords) RSF_CUDA(cudaMemcpyAsync(coords, dc.p, (size_t)nblk * 3 * sizeof(short), cudaMemcpyDeviceToHost, g->stream));
+  if (tsdf) RSF_CUDA(cudaMemcpyAsync(tsdf, dt.p, nv * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  if (rgbw) RSF_CUDA(cudaMemcpyAsync(rgbw, dr.p, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+  if (prob) RSF_CUDA(cudaMemcpyAsync(prob, dp.p, nv * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+uint32_t rsf_hash(int16_t x, int16_t y, int16_t z, uint32_t mask) { return hash_block(S3{x, y, z}, mask); }
+uint32_t rsf_shard_owner(int16_t x, int16_t y, int16_t z, int shift, int world) {
+  if (world <= 1) return 0;
+  return shard_owner(S3{x, y, z}, shift, world);
+}
+
+int rsf_allocate_blocks(rsf_grid_t g, const int16_t* block_coords, int n) {
+  if (int rc = check_grid(g)) return rc;
+  if (n < 0 || (n > 0 && !block_coords)) return fail(RSF_ERR_INVALID, "bad block_coords / n");
+  DeviceGuard dg(g->device);
+  DevBuf<short> dc(g->stream);
+  RSF_CUDA(dc.alloc((size_t)n * 3));
+  RSF_CUDA(cudaMemcpyAsync(dc.p, block_coords, (size_t)n * 3 * sizeof(short), cudaMemcpyHostToDevice, g->stream));
+  launch_allocate_coords(g->view, dc.p, n, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  return sync_counters(g);
+}
+
+int rsf_delete_blocks(rsf_grid_t g, const int16_t* block_coords, int n) {
+  if (int rc = check_grid(g)) return rc;
+  if (n < 0 || (n > 0 && !block_coords)) return fail(RSF_ERR_INVALID, "bad block_coords / n");
+  DeviceGuard dg(g->device);
+  DevBuf<short> dc(g->stream);
+  RSF_CUDA(dc.alloc((size_t)n * 3));
+  RSF_CUDA(cudaMemcpyAsync(dc.p, block_coords, (size_t)n * 3 * sizeof(short), cudaMemcpyHostToDevice, g->stream));
+  launch_delete_coords(g->view, dc.p, n, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  return sync_counters(g);
+}
+
+int rsf_retrieve_voxels(rsf_grid_t g, const int16_t* voxel_coords, int n, float* tsdf, uint8_t* rgbw, float* prob,
+                        uint8_t* found) {
+  if (int rc = check_grid(g)) return rc;
+  if (n < 0 || (n > 0 && !voxel_coords)) return fail(RSF_ERR_INVALID, "bad voxel_coords / n");
+  DeviceGuard dg(g->device);
+  DevBuf<short> dc(g->stream);
+  DevBuf<float> dt(g->stream), dp(g->stream);
+  DevBuf<uint32_t> dr(g->stream);
+  DevBuf<uint8_t> df(g->stream);
+  RSF_CUDA(dc.alloc((size_t)n * 3));
+  RSF_CUDA(dt.alloc(n));
+  RSF_CUDA(dp.alloc(n));
+  RSF_CUDA(dr.alloc(n));
+  RSF_CUDA(df.alloc(n));
+  RSF_CUDA(cudaMemcpyAsync(dc.p, voxel_coords, (size_t)n * 3 * sizeof(short), cudaMemcpyHostToDevice, g->stream));
+  launch_retrieve_voxels(g->view, dc.p, n, dt.p, dr.p, dp.p, df.p, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (tsdf) RSF_CUDA(cudaMemcpyAsync(tsdf, dt.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  if (rgbw) RSF_CUDA(cudaMemcpyAsync(rgbw, dr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, g->stream));
+  if (prob) RSF_CUDA(cudaMemcpyAsync(prob, dp.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  if (found) RSF_CUDA(cudaMemcpyAsync(found, df.p, (size_t)n, cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+int rsf_assign_voxels(rsf_grid_t g, const int16_t* voxel_coords, int n, const float* tsdf, const uint8_t* rgbw,
+                      const float* prob, uint8_t* written) {
+  if (int rc = check_grid(g)) return rc;
+  if (n < 0 || (n > 0 && !voxel_coords)) return fail(RSF_ERR_INVALID, "bad voxel_coords / n");
+  DeviceGuard dg(g->device);
+  DevBuf<short> dc(g->stream);
+  DevBuf<float> dt(g->stream), dp(g->stream);
+  DevBuf<uint32_t> dr(g->stream);
+  DevBuf<uint8_t> dw(g->stream);
+  RSF_CUDA(dc.alloc((size_t)n * 3));
+  RSF_CUDA(dw.alloc(n));
+  RSF_CUDA(cudaMemcpyAsync(dc.p, voxel_coords, (size_t)n * 3 * sizeof(short), cudaMemcpyHostToDevice, g->stream));
+  if (tsdf) {
+    RSF_CUDA(dt.alloc(n));
+    RSF_CUDA(cudaMemcpyAsync(dt.p, tsdf, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  }
+  if (rgbw) {
+    RSF_CUDA(dr.alloc(n));
+    RSF_CUDA(cudaMemcpyAsync(dr.p, rgbw, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
+  }
+  if (prob) {
+    RSF_CUDA(dp.alloc(n));
+    RSF_CUDA(cudaMemcpyAsync(dp.p, prob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  }
+  launch_assign_voxels(g->view, dc.p, n, dt.p, dr.p, dp.p, dw.p, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (written) RSF_CUDA(cudaMemcpyAsync(written, dw.p, (size_t)n, cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+int rsf_retrieve_tsdf_trilinear(rsf_grid_t g, const float* points, int n, float* tsdf) {
+  if (int rc = check_grid(g)) return rc;
+  if (n < 0 || (n > 0 && (!points || !tsdf))) return fail(RSF_ERR_INVALID, "bad points / tsdf / n");
+  DeviceGuard dg(g->device);
+  DevBuf<float> dpnt(g->stream), dout(g->stream);
+  RSF_CUDA(dpnt.alloc((size_t)n * 3));
+  RSF_CUDA(dout.alloc(n));
+  RSF_CUDA(cudaMemcpyAsync(dpnt.p, points, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  launch_trilinear(g->view, dpnt.p, n, dout.p, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  RSF_CUDA(cudaMemcpyAsync(tsdf, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+int rsf_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(RSF_ERR_INVALID, "ptr must not be NULL");
+  RSF_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return RSF_OK;
+}
+int rsf_host_free(void* ptr) {
+  if (ptr) RSF_CUDA(cudaFreeHost(ptr));
+  return RSF_OK;
+}
+
+}  // extern "C"

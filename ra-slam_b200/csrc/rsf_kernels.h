@@ -1,0 +1,28 @@
+// rsf_kernels.h -- host-callable launch wrappers of the kernels in rsf_kernels.cu.
+#pragma once
+#include <algorithm>
+
+#include "rsf_device.cuh"
+
+namespace rsf {
+
+void launch_init_pool(const GridView& g, cudaStream_t s);
+void launch_allocate(const GridView& g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
+                     const float* lt, float4* frame, cudaStream_t s);
+void launch_select_visible(const GridView& g, const Frame& f, int sm_count, cudaStream_t s);
+void launch_integrate(const GridView& g, const Frame& f, const float4* frame, int sm_count, cudaStream_t s);
+void launch_raycast(const GridView& g, const Frame& f, float step_size, uchar4* rgba, uchar4* normal, float* depth,
+                    float* prob, cudaStream_t s);
+void launch_gather_select(const GridView& g, int mode, int owned_only, S3 lo, S3 hi, int sm_count, cudaStream_t s);
+void launch_download_rows(const GridView& g, float vs, int nblk, int ncol, float* rows, int sm_count, cudaStream_t s);
+void launch_export_blocks(const GridView& g, int nblk, short* coords, float* tsdf, uint32_t* rgbw, float* prob,
+                          int sm_count, cudaStream_t s);
+void launch_allocate_coords(const GridView& g, const short* coords, int n, int sm_count, cudaStream_t s);
+void launch_delete_coords(const GridView& g, const short* coords, int n, cudaStream_t s);
+void launch_retrieve_voxels(const GridView& g, const short* pts, int n, float* tsdf, uint32_t* rgbw, float* prob,
+                            uint8_t* found, cudaStream_t s);
+void launch_assign_voxels(const GridView& g, const short* pts, int n, const float* tsdf, const uint32_t* rgbw,
+                          const float* prob, uint8_t* written, cudaStream_t s);
+void launch_trilinear(const GridView& g, const float* pts, int n, float* out, cudaStream_t s);
+
+}  // namespace rsf

@@ -1,0 +1,207 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle on the
+same seeded inputs (SURVEY.md Appendix B tolerances), plus size-independent properties."""
+import numpy as np
+import pytest
+
+import parity
+from oracle_lib import OracleGrid
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- the reference's own unit tests, re-expressed against the new table (voxel_hash_test.cu) ----
+def test_voxel_hash_single(rsf):
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=4096, table_slots_log2=14)
+    g.AllocateBlocks([[1, 1, 1]])
+    assert g.NumActiveBlock() == 1
+    assert g.Retrieve([[8, 8, 8]])["found"][0]
+    r = g.Retrieve([[0, 0, 0]])
+    assert not r["found"][0] and r["rgbw"][0, 3] == 0 and r["tsdf"][0] == -10 and r["prob"][0] == 0
+    g.AllocateBlocks([[0, 0, 0]])
+    for i in range(8):
+        assert g.Assign([[0, 0, i]], rgbw=[[i, i, i, i]])[0]
+    assert g.NumActiveBlock() == 2
+    for i in range(8):
+        assert g.Retrieve([[0, 0, i]])["rgbw"][0].tolist() == [i, i, i, i]
+
+
+def test_voxel_hash_multiple(rsf):
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=4096, table_slots_log2=14)
+    blocks = np.array([[i, i, i] for i in range(128)], np.int16)
+    g.AllocateBlocks(blocks)
+    assert g.NumActiveBlock() == 128
+    vals = np.array([[i, i, i, i] for i in range(128)], np.uint8)
+    assert g.Assign(blocks * 8, rgbw=vals).all()
+    assert np.array_equal(g.Retrieve(blocks * 8)["rgbw"], vals)
+    c = g.ExportBlocks()[0]
+    assert np.array_equal(c, blocks[np.argsort(rsf.block_keys(blocks))])
+
+
+def test_voxel_hash_collision(rsf):
+    # golden vectors of voxel_hash_test.cu:130-135 on the default-size table (2^22 slots, mask 2^21-1
+    # for the exported Hash); one pass allocates all four (ideal semantics)
+    g = rsf.TSDFGrid(0.01, 0.06)
+    blocks = np.array([[33, 180, 42], [61, 16, 170], [63, 171, 45], [0, 0, 0]], np.int16)
+    for _ in range(3):
+        g.AllocateBlocks(blocks)
+        assert g.NumActiveBlock() == 4
+    vals = np.array([[i, i, i, i] for i in range(4)], np.uint8)
+    assert g.Assign(blocks * 8, rgbw=vals).all()
+    assert np.array_equal(g.Retrieve(blocks * 8)["rgbw"], vals)
+
+
+def test_table_heavy_collisions_and_duplicates(rsf):
+    # tiny table: long probe chains, duplicate requests in one launch, delete + re-insert (ghost reuse)
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=2048, table_slots_log2=12)
+    rng = np.random.default_rng(0)
+    blocks = np.unique(rng.integers(-40, 40, size=(1500, 3)).astype(np.int16), axis=0)
+    g.AllocateBlocks(np.concatenate([blocks, blocks[::-1], blocks]))
+    assert g.NumActiveBlock() == len(blocks)
+    assert g.Retrieve(blocks * 8 + 3)["found"].all()
+    g.DeleteBlocks(np.concatenate([blocks[::2], blocks[::2]]))
+    assert g.NumActiveBlock() == len(blocks) - len(blocks[::2])
+    f = g.Retrieve(blocks * 8)["found"]
+    assert not f[::2].any() and f[1::2].all()
+    g.AllocateBlocks(blocks)
+    assert g.NumActiveBlock() == len(blocks)
+    c, t, w, p = g.ExportBlocks()
+    assert np.array_equal(c, blocks[np.argsort(rsf.block_keys(blocks))])
+    assert (w[..., 3] == 1).all() and (t == -1).all() and (p == 0.5).all()       # voxel_mem.cu:48-50
+
+
+def test_pool_exhaustion_is_an_error_not_ub(rsf):
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=64, table_slots_log2=10)
+    blocks = np.array([[i, 0, 0] for i in range(100)], np.int16)
+    with pytest.raises(rsf.RsfError) as e:
+        g.AllocateBlocks(blocks)
+    assert e.value.code == rsf.RSF_ERR_POOL_FULL
+    assert g.NumActiveBlock() == 64
+
+
+def test_trilinear_matches_oracle(rsf):
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=4096, table_slots_log2=14)
+    o = OracleGrid(0.01, 0.06, 1)
+    blocks = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 1]], np.int16)
+    g.AllocateBlocks(blocks)
+    o.AllocateBlocks(blocks)
+    rng = np.random.default_rng(3)
+    pts = np.array([[x, y, z] for x in range(16) for y in range(16) for z in range(16)], np.int16)
+    vals = rng.uniform(-1, 1, len(pts)).astype(np.float32)
+    g.Assign(pts, tsdf=vals)
+    o.Assign(pts, tsdf=vals)
+    q = rng.uniform(-1, 17, size=(400, 3)).astype(np.float32)
+    assert np.array_equal(g.RetrieveTSDF(q), o.RetrieveTSDF(q))
+
+
+# ---- Integrate / RayCast / Gather parity ----------------------------------------------------------
+def _run_both(rsf, seq, n, raycast_at=(), **gridkw):
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation, **gridkw)
+    o = OracleGrid(seq.voxel_size, seq.truncation, 0)
+    cam = rsf.CameraParams(seq.K, seq.H, seq.W)
+    rays = []
+    for i in range(n):
+        fr = seq.frame(i)
+        g.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        o.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        sg, so = g.stats(), o.stats()
+        for k in ("new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "active_blocks"):
+            assert sg[k] == so[k], (i, k, sg, so)
+        if i in raycast_at:
+            rays.append((g.RayCast(seq.max_depth * 2, cam, seq.poses[i]), o.RayCast(seq.max_depth * 2, cam, seq.poses[i])))
+    return g, o, rays
+
+
+@pytest.mark.parametrize("trunc", [0.04, 0.06])
+def test_integrate_parity_config1_small(rsf, synth, trunc):
+    seq = synth.config1(n_frames=100, H=120, W=160, truncation=trunc)
+    g, o, _ = _run_both(rsf, seq, 30)
+    m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
+    parity.assert_block_parity(m)
+    assert m["tsdf_bit_mismatch"] == 0 and m["rgb_mismatch"] == 0, m   # IEEE ops only: bit-exact
+
+
+def test_integrate_raycast_parity_config2(rsf, synth):
+    # TUM fr1-shaped: quantised depth, hand-held walk, integrate + raycast (max_depth * 2) per frame
+    seq = synth.config2(n_frames=300, H=240, W=320)
+    g, o, rays = _run_both(rsf, seq, 40, raycast_at=(19, 39))
+    m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
+    parity.assert_block_parity(m)
+    for rg, ro in rays:
+        r = parity.compare_raycast(rg, ro, seq.voxel_size)
+        assert r["hit_b"] > 0.5 * seq.H * seq.W
+        assert r["hit_mask_mismatch"] == 0, r
+        assert r["depth_max_vox"] <= 0.5, r           # north-star tolerance: <= 0.5 voxel
+        assert r["prob_max_abs"] <= 1e-5, r
+        assert r["rgba_max_abs"] <= 1 and r["normal_max_abs"] <= 1, r
+
+
+def test_integrate_parity_full_resolution(rsf, synth):
+    # 640x480 at the reference's intrinsics; fewer frames so the oracle finishes in seconds
+    seq = synth.config1(n_frames=100)
+    g, o, rays = _run_both(rsf, seq, 16, raycast_at=(15,))
+    m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
+    parity.assert_block_parity(m)
+    r = parity.compare_raycast(*rays[0], seq.voxel_size)
+    assert r["hit_mask_mismatch"] == 0 and r["depth_max_vox"] <= 0.5, r
+
+
+def test_gather_parity(rsf, synth):
+    seq = synth.config3(n_frames=200)
+    seq.H, seq.W, seq.K = 120, 160, synth.scaled(seq.K, 0.25, 0.25)
+    g, o, _ = _run_both(rsf, seq, 12)
+
+    def canon(rows):
+        key = np.round(rows[:, :3] / seq.voxel_size).astype(np.int64)
+        order = np.lexsort((key[:, 0], key[:, 1], key[:, 2]))
+        return rows[order]
+
+    for name in ("GatherValid", "GatherValidSemantic"):
+        a, b = canon(getattr(g, name)()), canon(getattr(o, name)())
+        assert a.shape == b.shape
+        assert np.array_equal(a[:, :4], b[:, :4])          # xyz + tsdf bit-exact
+        if a.shape[1] == 5:
+            assert np.abs(a[:, 4] - b[:, 4]).max() <= 1e-5
+    c = g.ExportBlocks()[0].astype(np.float32) * 8 * seq.voxel_size
+    lo, hi = c.min(axis=0), c.max(axis=0) + 8 * seq.voxel_size
+    mid = 0.5 * (lo + hi)
+    vol = rsf.BoundingCube(lo[0], mid[0], lo[1], hi[1], mid[2], hi[2])
+    a, b = canon(g.GatherVoxels(vol)), canon(o.GatherVoxels(vol))
+    assert len(a) > 0 and np.array_equal(a, b)
+
+
+def test_semantic_properties(rsf, synth):
+    seq = synth.config1(n_frames=100, H=120, W=160)
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    for i in range(6):
+        rgb, d, _, _ = seq.frame(i)
+        ones = np.ones_like(d)
+        g.Integrate(rgb, d, ones, ones, seq.max_depth, seq.K, seq.poses[i])
+    c, t, w, p = g.ExportBlocks()
+    assert (p == 0.5).all()                                # ht == lt => prob stays exactly 0.5
+    assert (w[..., 3] >= 1).all() and (w[..., 3] <= 40).all()
+    assert (np.abs(t) <= 1).all()
+    assert (np.abs(t).min(axis=1) < 0.9).all()             # every survivor passed the carve test
+
+
+def test_device_pointer_path_matches_host_path(rsf, synth):
+    import torch
+    seq = synth.config2(n_frames=300, H=120, W=160)
+    g1 = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    s = torch.cuda.current_stream()
+    g2 = rsf.TSDFGrid(seq.voxel_size, seq.truncation, stream=s.cuda_stream)
+    for i in range(10):
+        fr = seq.frame(i)
+        g1.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        g2.Integrate(*[torch.from_numpy(a).cuda() for a in fr], seq.max_depth, seq.K, seq.poses[i])
+    g2.synchronize()
+    a, b = g1.ExportBlocks(), g2.ExportBlocks()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    cam = rsf.CameraParams(seq.K, seq.H, seq.W)
+    r1 = g1.RayCast(8.0, cam, seq.poses[9])
+    out = {"rgba": torch.empty((seq.H, seq.W, 4), dtype=torch.uint8, device="cuda"),
+           "depth": torch.empty((seq.H, seq.W), dtype=torch.float32, device="cuda")}
+    g2.RayCast(8.0, cam, seq.poses[9], out=out)
+    g2.synchronize()
+    assert np.array_equal(out["rgba"].cpu().numpy(), r1["rgba"])
+    assert np.array_equal(out["depth"].cpu().numpy(), r1["depth"])

@@ -1,0 +1,116 @@
+"""CPU tests of host-side logic: pose/intrinsics PODs, the synthetic sequences, sharded fusion
+merge over gloo (world_size 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle_lib import OracleGrid
+
+
+def test_se3_from_matrix_roundtrip(rsf):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        T = rsf.SE3(q, rng.normal(size=3))
+        T2 = rsf.SE3.from_matrix(T.matrix())
+        assert np.allclose(T2.rotation_matrix(), T.rotation_matrix(), atol=1e-5)
+        assert np.allclose((T * T.Inverse()).matrix(), np.eye(4), atol=1e-5)
+
+
+def test_synth_is_deterministic_and_well_formed(synth):
+    seq = synth.config2(n_frames=5, H=60, W=80)
+    a, b = seq.frame(3), seq.frame(3)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    rgb, d, ht, lt = a
+    assert rgb.dtype == np.uint8 and rgb.shape == (60, 80, 3)
+    assert d.dtype == ht.dtype == lt.dtype == np.float32 and d.shape == (60, 80)
+    assert (d > 0).all() and d.max() < 10
+    assert np.allclose(ht + lt, 1)
+    # depth went through uint16 / 5000 (configs/TUM_RGBD_rgbd_1.yaml:44)
+    assert np.allclose(np.round(d * 5000) / 5000, d, atol=1e-6)
+
+
+def test_synth_depth_is_z_depth(synth, rsf):
+    # back-project with the generated depth and check the points lie on scene surfaces
+    seq = synth.config1(n_frames=4, H=48, W=64)
+    _, d, _, _ = seq.frame(1)
+    T = seq.poses[1]
+    ys, xs = np.mgrid[0:48, 0:64]
+    pc = np.stack([(xs - seq.K.cx) / seq.K.fx * d, (ys - seq.K.cy) / seq.K.fy * d, d], -1)
+    pw = (pc - T.t) @ T.rotation_matrix()
+    sc = seq.scene
+    on_room = np.min(np.minimum(np.abs(pw - sc.room_min), np.abs(pw - sc.room_max)), axis=-1) < 1e-3
+    on_box = np.zeros_like(on_room)
+    for lo, hi in sc.boxes:
+        inside = np.all((pw > lo - 1e-3) & (pw < hi + 1e-3), axis=-1)
+        near = np.min(np.minimum(np.abs(pw - lo), np.abs(pw - hi)), axis=-1) < 1e-3
+        on_box |= inside & near
+    assert (on_room | on_box).mean() > 0.999
+
+
+def _sharded_worker(rank, world, port, H, W, n, q):
+    import importlib
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import rsfusion
+    synth = importlib.import_module("ra-slam_b200.synth")
+    shardlib = importlib.import_module("ra-slam_b200.sharding")
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seq = synth.config2(n_frames=300, H=H, W=W)
+    g = OracleGrid(seq.voxel_size, seq.truncation, 1)
+    g.set_shard(rank, world, 1, 1)
+    for i in range(n):
+        # frame broadcast from the ingest rank (rank 0), as the sharded path does over NCCL
+        if rank == 0:
+            fr = [torch.from_numpy(a.copy()) for a in seq.frame(i)]
+        else:
+            fr = [torch.empty((H, W, 3), dtype=torch.uint8)] + [torch.empty((H, W), dtype=torch.float32) for _ in range(3)]
+        shardlib.broadcast_frame(fr, src=0)
+        g.Integrate(*[t.numpy() for t in fr], seq.max_depth, seq.K, seq.poses[i])
+    cam = rsfusion.CameraParams(seq.K, H, W)
+    r = g.RayCast(seq.max_depth * 2, cam, seq.poses[n - 1])
+    merged = shardlib.merge_raycast_min_depth({k: torch.from_numpy(v) for k, v in r.items()})
+    owned = g.ExportBlocks(owned_only=True)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, owned[0])
+    if rank == 0:
+        q.put(({k: v.numpy() for k, v in merged.items()}, gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_fusion_merges_to_single_grid_over_gloo(synth, rsf):
+    """world_size-2 gloo run of the sharded data flow (frame broadcast, owned-block integration,
+    per-pixel min-depth merge) on the oracle: merged == unsharded."""
+    import torch.multiprocessing as mp
+    H, W, n, world = 60, 80, 14, 2
+    seq = synth.config2(n_frames=300, H=H, W=W)
+    single = OracleGrid(seq.voxel_size, seq.truncation, 2)
+    for i in range(n):
+        single.Integrate(*seq.frame(i), seq.max_depth, seq.K, seq.poses[i])
+    ref = single.RayCast(seq.max_depth * 2, rsf.CameraParams(seq.K, H, W), seq.poses[n - 1])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, H, W, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    merged, gathered = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # ownership is a partition of the unsharded block set
+    allc = np.concatenate(gathered)
+    keys = rsf.block_keys(allc)
+    assert len(np.unique(keys)) == len(keys)
+    assert set(keys.tolist()) == set(rsf.block_keys(single.ExportBlocks()[0]).tolist())
+    # merged raycast equals the single-grid raycast
+    assert np.array_equal(merged["depth"] > 0, ref["depth"] > 0)
+    assert np.allclose(merged["depth"], ref["depth"], atol=1e-6)
+    assert np.array_equal(merged["rgba"], ref["rgba"])
