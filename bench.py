@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the TSDF fusion hot path (integrate + raycast per frame) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A step = one frame of the workload: TSDFGrid::Integrate of a 640x480 RGB + depth + ht/lt frame
+followed by TSDFGrid::RayCast from the same pose at max_depth*2 (TSDFSystem::Render,
+modules/tsdf_module.cc:45-49).  Workload = BASELINE.json configs[1]: TUM fr1-shaped synthetic
+sequence (configs/TUM_RGBD_rgbd_1.yaml intrinsics, depth through uint16/5000, hand-held walk,
+voxel 0.01 m, truncation 0.06 m, max_depth 4 m, seed 1).  W warm-up frames build the local map,
+then exactly K further, distinct frames are timed.
+
+value  : frames/s with the frames already resident in HBM (rsf_integrate_device +
+         rsf_raycast_device), CUDA events around each step on the launching stream, L2 flushed
+         (256 MiB memset) between steps outside the events.
+e2e    : frames/s through the blocking host entry points rsf_integrate + rsf_raycast with pinned
+         HOST buffers (H2D of the frame and D2H of rgba+normal+depth inside the timed region),
+         wall clock bracketed by synchronisation.
+roofline : the integrate kernel (HBM-bound voxel read-modify-write), algorithmic bytes
+         / CUDA-event duration measured by the library's per-kernel events in the same timed region.
+cpu_baseline : the CPU oracle (multithreaded C++ restatement of the reference algorithm; the
+         reference has no CPU path of its own) on a bounded sample of the same sequence.
+
+N > 1 (torchrun): independent sequences, one grid per GPU (BASELINE.json configs[3] pattern), no
+data-path collective; weak scaling; value = all ranks' frames / max-over-ranks time.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/s integrate+raycast 640x480 semantic (TUM fr1-shaped)"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--cpu-sample-frames", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def make_sequence(args, rank, n_frames):
+    synth = importlib.import_module("ra-slam_b200.synth")
+    seq = synth.config2(n_frames=max(n_frames, 300), H=args.height, W=args.width)
+    if rank:   # independent sequence per replica: same scene family, different seed
+        sc = synth.room_scene(size=(5.0, 4.0, 2.8), n_boxes=4, seed=1 + 100 * rank)
+        seq.scene = sc
+        seq.poses = synth.handheld_trajectory(sc, max(n_frames, 300), seed=1 + 100 * rank)
+    return seq
+
+
+def render_frames(seq, n):
+    """Pre-render n frames (CPU, numpy) -- outside every timed region."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as ex:
+        return list(ex.map(seq.frame, range(n)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.idx, self.proc = [], gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                mx = float(p[2])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(p[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "integrate_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_oracle_fps(seq, frames, warm, sample, threads=0):
+    """integrate+raycast frames/s of the CPU oracle on `sample` frames after `warm` map-building frames."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import OracleGrid
+    rsf = importlib.import_module("ra-slam_b200")
+    g = OracleGrid(seq.voxel_size, seq.truncation, threads)
+    cam = rsf.CameraParams(seq.K, seq.H, seq.W)
+    for i in range(warm):
+        g.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
+    t0 = time.perf_counter()
+    ti = tr = 0.0
+    n = 0
+    for i in range(warm, warm + sample):
+        a = time.perf_counter()
+        g.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
+        b = time.perf_counter()
+        g.RayCast(seq.max_depth * 2, cam, seq.poses[i])
+        c = time.perf_counter()
+        ti += b - a
+        tr += c - b
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, {"integrate_ms": 1e3 * ti / n, "raycast_ms": 1e3 * tr / n}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the box's host cores (CPU oracle port; the
+    reference has no CPU path and does not build offline)."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    # bounded sample: each step is one frame; cap the run to a few minutes of CPU work
+    K = min(K, 60)
+    W = min(W, 20)
+    seq = make_sequence(args, 0, W + K)
+    frames = render_frames(seq, W + K)
+    cores = os.cpu_count() or 1
+    fps, br = cpu_oracle_fps(seq, frames, W, K, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame", "height": seq.H,
+                   "width": seq.W, "voxel_size": seq.voxel_size, "truncation": seq.truncation,
+                   "max_depth": seq.max_depth, "parallelism": "host threads"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{K} frames after {W} map-building frames, oracle/rsf_oracle.cpp, {cores} threads",
+                         **br},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_native(args):
+    import torch
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    rsf = importlib.import_module("ra-slam_b200")
+    K, W = args.steps, args.warmup
+    n = W + K
+    seq = make_sequence(args, rank, n)
+    frames = render_frames(seq, n)
+    H, Wd = seq.H, seq.W
+    P = H * Wd
+    cam = rsf.CameraParams(seq.K, H, Wd)
+    rmax = seq.max_depth * 2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm (value) ------------------------------------------------
+    stream = torch.cuda.current_stream()
+    grid = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank, stream=stream.cuda_stream)
+    d_frames = [tuple(torch.from_numpy(a).to(dev) for a in fr) for fr in frames]
+    out = {"rgba": torch.empty((H, Wd, 4), dtype=torch.uint8, device=dev),
+           "normal": torch.empty((H, Wd, 4), dtype=torch.uint8, device=dev),
+           "depth": torch.empty((H, Wd), dtype=torch.float32, device=dev)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_dev(i):
+        grid.Integrate(*d_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid.RayCast(rmax, cam, seq.poses[i], out=out)
+
+    for i in range(W):
+        step_dev(i)
+    grid.synchronize()
+    tot0 = grid.totals()
+    grid.profile_enable(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.time()
+    for k in range(K):
+        flush.zero_()                     # L2 flush, outside the timed events
+        ev[k][0].record()
+        step_dev(W + k)
+        ev[k][1].record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    prof = grid.profile_read()
+    grid.profile_enable(False)
+    tot1 = grid.totals()
+    stats_end = grid.stats()
+
+    # the same K frames again, L2 left warm (informational)
+    grid_w = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank, stream=stream.cuda_stream)
+    for i in range(W):
+        grid_w.Integrate(*d_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid_w.RayCast(rmax, cam, seq.poses[i], out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        grid_w.Integrate(*d_frames[W + k], seq.max_depth, seq.K, seq.poses[W + k])
+        grid_w.RayCast(rmax, cam, seq.poses[W + k], out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    warm_ms = e0.elapsed_time(e1)
+    grid_w.close()
+    del d_frames
+
+    # ---------------- end-to-end arm (e2e): blocking host API, pinned host buffers ----------------
+    grid_e = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank)
+    pins = []
+    h_frames = []
+    for fr in frames:
+        row = []
+        for a in fr:
+            pa = rsf.PinnedArray(a.shape, a.dtype)
+            pa.array[...] = a
+            pins.append(pa)
+            row.append(pa.array)
+        h_frames.append(tuple(row))
+    h_out = {}
+    for kname, shape, dt in (("rgba", (H, Wd, 4), np.uint8), ("normal", (H, Wd, 4), np.uint8), ("depth", (H, Wd), np.float32)):
+        pa = rsf.PinnedArray(shape, dt)
+        pins.append(pa)
+        h_out[kname] = pa.array
+
+    def step_e2e(i):
+        grid_e.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid_e.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_out)
+
+    for i in range(W):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        step_e2e(W + k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    checksum = float(h_out["depth"].sum())
+    grid_e.close()
+
+    # ---------------- max over ranks ---------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([dev_ms, warm_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, warm_ms, e2e_s = (float(x) for x in t.tolist())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the integrate kernel ---------------------------------------------
+    upd = tot1["updated_voxels"] - tot0["updated_voxels"]
+    vis = tot1["visible_blocks"] - tot0["visible_blocks"]
+    int_ms, int_n = prof["integrate"]
+    # 24 B per updated voxel (12 read + 12 written: tsdf, rgbw, prob) + 12 B per visible
+    # block descriptor + compulsory image reads (7 + 4K) B per pixel, K = 2 -> 15 B
+    alg_bytes = 24.0 * upd + 12.0 * vis + 15.0 * P * int_n
+    peak, peak_src = measured_peak_gbs()
+    achieved = alg_bytes / (int_ms * 1e-3) / 1e9 if int_ms > 0 else 0.0
+    kernels = {k: {"ms_per_launch": (v[0] / v[1] if v[1] else None), "launches": v[1],
+                   "share_of_step": (v[0] / dev_ms if dev_ms else None)} for k, v in prof.items()}
+    line = {
+        "metric": METRIC, "value": world * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame", "height": H, "width": Wd,
+                   "voxel_size": seq.voxel_size, "truncation": seq.truncation, "max_depth": seq.max_depth,
+                   "raycast_max_depth": rmax, "semantic_classes": 2,
+                   "l2": "flushed: 256 MiB memset between steps, outside the timed events",
+                   "parallelism": f"replicas x{world} (independent sequences, no collective)" if world > 1 else "1 grid"},
+        "value_warm_l2": world * K / (warm_ms * 1e-3),
+        "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 12 * P,
+                "ms_per_step": 1e3 * e2e_s / K, "api": "rsf_integrate + rsf_raycast (blocking, pinned host buffers)",
+                "checksum": checksum},
+        # per frame: begin_frame, allocate, select_visible, integrate, tile_range, raycast
+        "gpu_launches": int(sum(v[1] for v in prof.values()) + int_n + prof["raycast"][1]),
+        "roofline": {"kernel": "integrate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes / max(int_n, 1),
+                     "updated_voxels_per_launch": upd / max(int_n, 1), "visible_blocks_per_launch": vis / max(int_n, 1),
+                     "voxel_updates_per_s": upd / (int_ms * 1e-3) if int_ms else None},
+        "kernels": kernels,
+        "clocks": clocks,
+        "map": {"active_blocks": stats_end["active_blocks"], "high_water": stats_end["high_water"]},
+    }
+    if not args.no_cpu_baseline:
+        s = min(args.cpu_sample_frames, K)
+        cores = os.cpu_count() or 1
+        fps, br = cpu_oracle_fps(seq, frames, W, s, cores)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{s} frames after {W} map-building frames, oracle/rsf_oracle.cpp "
+                                          f"(multithreaded restatement; the reference has no CPU path)", **br}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

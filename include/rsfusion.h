@@ -50,6 +50,9 @@ enum rsf_status {
 
 typedef struct rsf_grid_s* rsf_grid_t;
 
+/* rsf_options.flags: use rsf_options.stream as given even when it is NULL (the legacy default stream). */
+#define RSF_FLAG_EXTERNAL_STREAM 1u
+
 /* Construction parameters.  voxel_size/truncation are the two arguments of
  * TSDFGrid::TSDFGrid (voxel_tsdf.cu:376-377); the rest replace compile-time #defines of the
  * reference (NUM_BLOCK voxel_mem.cuh:11-13, NUM_ENTRY voxel_hash.cuh:13-25, MAX_IMG_SIZE
@@ -66,7 +69,7 @@ typedef struct rsf_options {
   int shard_shift;         /*   owner = mix(block_pos >> shift) % world; default 1          */
   int shard_halo;          /*   redundant halo in blocks; default 1                         */
   void* stream;            /* optional external cudaStream_t; NULL = library-owned stream   */
-  unsigned flags;          /* reserved, must be 0                                           */
+  unsigned flags;          /* RSF_FLAG_* bits                                               */
 } rsf_options;
 
 /* Per-frame counters of the last rsf_integrate* call (reference logs only block counts,
@@ -162,6 +165,17 @@ RSF_API int rsf_assign_voxels(rsf_grid_t g, const int16_t* voxel_coords, int n, 
                       const uint8_t* rgbw, const float* prob, uint8_t* written);
 /* VoxelHashTable::RetrieveTSDF (voxel_hash.cu:161-188) at n continuous grid points (n x 3 f32). */
 RSF_API int rsf_retrieve_tsdf_trilinear(rsf_grid_t g, const float* points, int n, float* tsdf);
+
+/* ---- measurement hooks (no reference equivalent; the reference only logs wall-clock ms,
+ * modules/tsdf_module.cc:108-112) --------------------------------------------------------------
+ * rsf_profile_enable(g, 1) brackets every subsequent kernel launch with a CUDA event pair on the
+ * grid's stream; rsf_profile_read synchronises and returns, per kernel, the summed duration [ms]
+ * and launch count since the last read / enable. */
+enum rsf_prof_kernel { RSF_PROF_ALLOCATE = 0, RSF_PROF_SELECT = 1, RSF_PROF_INTEGRATE = 2, RSF_PROF_RAYCAST = 3, RSF_PROF_NUM = 4 };
+RSF_API int rsf_profile_enable(rsf_grid_t g, int on);
+RSF_API int rsf_profile_read(rsf_grid_t g, double ms[RSF_PROF_NUM], int64_t launches[RSF_PROF_NUM]);
+/* Running totals since creation: {frames, new_blocks, visible_blocks, updated_voxels, carved_blocks}. */
+RSF_API int rsf_get_totals(rsf_grid_t g, int64_t totals[5]);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so callers can hand rsf_integrate /
  * rsf_raycast page-locked buffers and get true asynchronous DMA. */

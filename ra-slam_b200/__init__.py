@@ -78,6 +78,9 @@ ABI = {
     "rsf_retrieve_voxels": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "rsf_assign_voxels": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "rsf_retrieve_tsdf_trilinear": (C.c_int, [_P, _P, C.c_int, _P]),
+    "rsf_profile_enable": (C.c_int, [_P, C.c_int]),
+    "rsf_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "rsf_get_totals": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rsf_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "rsf_host_free": (C.c_int, [_P]),
 }
@@ -240,7 +243,9 @@ class TSDFGrid:
         o.voxel_size, o.truncation, o.device = voxel_size, truncation, device
         o.pool_blocks, o.table_slots_log2, o.max_pixels = pool_blocks, table_slots_log2, max_pixels
         o.shard_rank, o.shard_world, o.shard_shift, o.shard_halo = shard_rank, shard_world, shard_shift, shard_halo
-        o.stream = stream
+        if stream is not None:
+            o.stream = stream or None
+            o.flags = 1          # RSF_FLAG_EXTERNAL_STREAM: use it even if it is the default stream (0)
         self._h = _P()
         _check(self._lib.rsf_create(C.byref(o), C.byref(self._h)))
         self.voxel_size, self.truncation = float(voxel_size), float(truncation)
@@ -350,6 +355,23 @@ class TSDFGrid:
         s = rsf_frame_stats()
         _check(self._lib.rsf_get_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in rsf_frame_stats._fields_}
+
+    PROF_KERNELS = ("allocate", "select", "integrate", "raycast")
+
+    def profile_enable(self, on: bool = True):
+        _check(self._lib.rsf_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kernel: (total_ms, launches)} since the last read."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        _check(self._lib.rsf_profile_read(self._h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_KERNELS)}
+
+    def totals(self) -> dict:
+        t = (C.c_int64 * 5)()
+        _check(self._lib.rsf_get_totals(self._h, t))
+        return dict(zip(("frames", "new_blocks", "visible_blocks", "updated_voxels", "carved_blocks"), list(t)))
 
     def ExportBlocks(self, owned_only: bool = False, sort: bool = True):
         """(coords n x 3 i16, tsdf n x 512 f32, rgbw n x 512 x 4 u8, prob n x 512 f32); sorted by key."""

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "rsf_kernels.h"
 #include "rsfusion.h"
@@ -68,9 +69,14 @@ struct rsf_grid_s {
   // raycast outputs (device)
   uchar4 *d_rgba = nullptr, *d_normal = nullptr;
   float *d_rdepth = nullptr, *d_rprob = nullptr;
+  unsigned* d_ranges = nullptr;   // per-tile depth ranges of the raycast pre-pass
   // pinned mirror of the device counters
   Counters* h_ctr = nullptr;
   rsf_frame_stats last{};
+  // optional per-kernel CUDA-event timing (rsf_profile_*)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[RSF_PROF_NUM];
+  size_t prof_used[RSF_PROF_NUM] = {};
 };
 
 namespace {
@@ -118,12 +124,43 @@ int sync_counters(rsf_grid_t g) {
   return RSF_OK;
 }
 
+// RAII: brackets one kernel launch with a CUDA event pair when profiling is on
+struct ProfScope {
+  rsf_grid_t g;
+  cudaEvent_t stop = nullptr;
+  ProfScope(rsf_grid_t grid, int which) : g(grid) {
+    if (!g->profiling) return;
+    auto& v = g->prof_events[which];
+    size_t& used = g->prof_used[which];
+    if (used == v.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      v.emplace_back(a, b);
+    }
+    cudaEventRecord(v[used].first, g->stream);
+    stop = v[used].second;
+    ++used;
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, g->stream);
+  }
+};
+
 int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
                       const float* lt) {
-  RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrFrameOff, 0, kCtrFrameBytes, g->stream));
-  launch_allocate(g->view, f, rgb, depth, ht, lt, g->d_frame, g->stream);
-  launch_select_visible(g->view, f, g->sm_count, g->stream);
-  launch_integrate(g->view, f, g->d_frame, g->sm_count, g->stream);
+  launch_begin_frame(g->view, g->stream);
+  {
+    ProfScope p(g, RSF_PROF_ALLOCATE);
+    launch_allocate(g->view, f, rgb, depth, ht, lt, g->d_frame, g->stream);
+  }
+  {
+    ProfScope p(g, RSF_PROF_SELECT);
+    launch_select_visible(g->view, f, g->sm_count, g->stream);
+  }
+  {
+    ProfScope p(g, RSF_PROF_INTEGRATE);
+    launch_integrate(g->view, f, g->d_frame, g->sm_count, g->stream);
+  }
   RSF_CUDA(cudaGetLastError());
   return RSF_OK;
 }
@@ -210,7 +247,7 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   if (o.table_slots_log2 > 30 || ((size_t)1 << o.table_slots_log2) < 2 * (size_t)o.pool_blocks)
     return fail(RSF_ERR_INVALID, "table_slots_log2=%d must give >= 2x pool_blocks=%d slots", o.table_slots_log2, o.pool_blocks);
   if (o.shard_rank < 0 || o.shard_rank >= o.shard_world) return fail(RSF_ERR_INVALID, "shard_rank outside [0, shard_world)");
-  if (o.flags != 0) return fail(RSF_ERR_INVALID, "flags must be 0");
+  if (o.flags & ~(unsigned)RSF_FLAG_EXTERNAL_STREAM) return fail(RSF_ERR_INVALID, "unknown bits in flags");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -232,7 +269,7 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   g->sm_count = prop.multiProcessorCount;
   g->table_slots = (size_t)1 << o.table_slots_log2;
   g->max_pixels = (size_t)o.max_pixels;
-  if (o.stream) {
+  if (o.stream || (o.flags & RSF_FLAG_EXTERNAL_STREAM)) {
     g->stream = (cudaStream_t)o.stream;
   } else {
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -248,12 +285,11 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   const size_t P = g->max_pixels;
   bool ok = true;
   auto A = [&](void** p, size_t bytes) { ok = ok && cudaMalloc(p, bytes) == cudaSuccess; };
-  A((void**)&v.keys, g->table_slots * sizeof(uint64_t));
-  A((void**)&v.vals, g->table_slots * sizeof(int));
+  A((void**)&v.table, g->table_slots * sizeof(TableEntry));
   A((void**)&v.pool, (size_t)o.pool_blocks * kSlabBytes);
   A((void**)&v.meta, (size_t)o.pool_blocks * sizeof(BlockMeta));
   A((void**)&v.heap, (size_t)o.pool_blocks * sizeof(int));
-  A((void**)&v.vis_list, (size_t)o.pool_blocks * sizeof(int));
+  A((void**)&v.vis_list, (size_t)o.pool_blocks * sizeof(VisEntry));
   A((void**)&v.gather_list, (size_t)o.pool_blocks * sizeof(int));
   A((void**)&v.ctr, sizeof(Counters));
   A((void**)&g->d_rgb, P * 3);
@@ -265,10 +301,11 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   A((void**)&g->d_normal, P * sizeof(uchar4));
   A((void**)&g->d_rdepth, P * sizeof(float));
   A((void**)&g->d_rprob, P * sizeof(float));
+  A((void**)&g->d_ranges, (P / 256 + 4096) * 2 * sizeof(unsigned) + 64);
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   if (ok) {
-    ok = ok && cudaMemsetAsync(v.keys, 0xff, g->table_slots * sizeof(uint64_t), g->stream) == cudaSuccess;
-    ok = ok && cudaMemsetAsync(v.vals, 0xff, g->table_slots * sizeof(int), g->stream) == cudaSuccess;
+    // key = kEmptyKey (all ones), val = kValFree (-1)
+    ok = ok && cudaMemsetAsync(v.table, 0xff, g->table_slots * sizeof(TableEntry), g->stream) == cudaSuccess;
     launch_init_pool(v, g->stream);
     ok = ok && cudaStreamSynchronize(g->stream) == cudaSuccess;
   }
@@ -286,11 +323,16 @@ int rsf_destroy(rsf_grid_t g) {
   DeviceGuard dg(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   GridView& v = g->view;
-  void* ptrs[] = {v.keys,   v.vals,     v.pool,     v.meta,    v.heap,    v.vis_list, v.gather_list, v.ctr,     g->d_rgb,
-                  g->d_depth, g->d_ht,  g->d_lt,    g->d_frame, g->d_rgba, g->d_normal, g->d_rdepth,  g->d_rprob};
+  void* ptrs[] = {v.table,  v.pool,     v.meta,    v.heap,    v.vis_list, v.gather_list, v.ctr,     g->d_rgb,
+                  g->d_depth, g->d_ht,  g->d_lt,    g->d_frame, g->d_rgba, g->d_normal, g->d_rdepth,  g->d_rprob, g->d_ranges};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
+  for (auto& v : g->prof_events)
+    for (auto& e : v) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return RSF_OK;
@@ -329,8 +371,11 @@ int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float 
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
   // step_size = truncation / 2, voxel_tsdf.cu:892
-  launch_raycast(g->view, f, g->opt.truncation / 2, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
-                 depth, prob, g->stream);
+  {
+    ProfScope p(g, RSF_PROF_RAYCAST);
+    launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, reinterpret_cast<uchar4*>(rgba),
+                   reinterpret_cast<uchar4*>(normal), depth, prob, g->sm_count, g->stream);
+  }
   RSF_CUDA(cudaGetLastError());
   return RSF_OK;
 }
@@ -341,8 +386,12 @@ int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float K[4], c
   Frame f;
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
-  launch_raycast(g->view, f, g->opt.truncation / 2, rgba ? g->d_rgba : nullptr, normal ? g->d_normal : nullptr,
-                 depth ? g->d_rdepth : nullptr, prob ? g->d_rprob : nullptr, g->stream);
+  {
+    ProfScope p(g, RSF_PROF_RAYCAST);
+    launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, rgba ? g->d_rgba : nullptr,
+                   normal ? g->d_normal : nullptr, depth ? g->d_rdepth : nullptr, prob ? g->d_rprob : nullptr,
+                   g->sm_count, g->stream);
+  }
   RSF_CUDA(cudaGetLastError());
   const size_t P = (size_t)H * W;
   if (rgba) RSF_CUDA(cudaMemcpyAsync(rgba, g->d_rgba, P * 4, cudaMemcpyDeviceToHost, g->stream));
@@ -522,6 +571,48 @@ int rsf_retrieve_tsdf_trilinear(rsf_grid_t g, const float* points, int n, float*
   RSF_CUDA(cudaGetLastError());
   RSF_CUDA(cudaMemcpyAsync(tsdf, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
   RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
+}
+
+int rsf_profile_enable(rsf_grid_t g, int on) {
+  if (int rc = check_grid(g)) return rc;
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  g->profiling = on != 0;
+  for (auto& u : g->prof_used) u = 0;
+  return RSF_OK;
+}
+
+int rsf_profile_read(rsf_grid_t g, double ms[RSF_PROF_NUM], int64_t launches[RSF_PROF_NUM]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!ms || !launches) return fail(RSF_ERR_INVALID, "ms / launches must not be NULL");
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  for (int k = 0; k < RSF_PROF_NUM; ++k) {
+    double sum = 0;
+    for (size_t i = 0; i < g->prof_used[k]; ++i) {
+      float t = 0.f;
+      RSF_CUDA(cudaEventElapsedTime(&t, g->prof_events[k][i].first, g->prof_events[k][i].second));
+      sum += t;
+    }
+    ms[k] = sum;
+    launches[k] = (int64_t)g->prof_used[k];
+    g->prof_used[k] = 0;
+  }
+  return RSF_OK;
+}
+
+int rsf_get_totals(rsf_grid_t g, int64_t totals[5]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!totals) return fail(RSF_ERR_INVALID, "totals must not be NULL");
+  DeviceGuard dg(g->device);
+  if (int rc = sync_counters(g)) return rc;
+  const Counters& c = *g->h_ctr;   // totals exclude the frame still held in the per-frame counters
+  totals[0] = (int64_t)c.tot_frames;
+  totals[1] = (int64_t)(c.tot_new_blocks + c.new_blocks);
+  totals[2] = (int64_t)(c.tot_visible_blocks + (unsigned long long)c.vis_count);
+  totals[3] = (int64_t)(c.tot_updated_voxels + c.updated_voxels);
+  totals[4] = (int64_t)(c.tot_carved_blocks + c.carved_blocks);
   return RSF_OK;
 }
 

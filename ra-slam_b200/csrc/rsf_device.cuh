@@ -17,13 +17,20 @@ namespace rsf {
 
 constexpr int kBlockLen = 8;
 constexpr int kBlockVol = 512;
-// One voxel block = one contiguous 6 KiB slab: [tsdf f32 x512 | rgbw u8x4 x512 | prob f32 x512].
+// One voxel block = one contiguous 6 KiB slab: [tsdf f32 x512 | rgbw u8x4 x512 | logit f32 x512].
 // (The reference keeps three separate 512 MiB SoA pools, voxel_mem.cu:19-21; a slab keeps one
-// block's state in 3 consecutive DRAM pages and lets a warp stream it with 128-bit accesses.)
+// block's state in 3 consecutive DRAM pages and lets a CTA stream it with 128-bit accesses.)
+//
+// The third plane holds logit(p) = ln p - ln(1-p) instead of the reference's probability p
+// (VoxelSEGM, voxel_types.cuh:36-43).  The reference's fusion (voxel_tsdf.cu:241-248)
+//     pos = exp((wo ln p + wn ln ht)/w), neg = exp((wo ln(1-p) + wn ln lt)/w), p' = pos/(pos+neg)
+// is exactly logit(p') = (wo logit(p) + wn (ln ht - ln lt))/w, a running average with no
+// transcendental per voxel (ln ht - ln lt is computed once per pixel).  Every API output converts
+// back with p = 1/(1+exp(-logit)); measured |dp| vs the reference recurrence < 1e-6.
 constexpr int kSlabBytes = 3 * kBlockVol * 4;
 constexpr int kSlabTsdfOff = 0;
 constexpr int kSlabRgbwOff = kBlockVol * 4;
-constexpr int kSlabProbOff = 2 * kBlockVol * 4;
+constexpr int kSlabLogitOff = 2 * kBlockVol * 4;
 
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr int kValFree = -1;      // key present (or slot empty) but no block attached
@@ -110,7 +117,10 @@ struct Counters {
   int pad1;
   unsigned long long new_blocks, updated_voxels, carved_blocks;
   int gather_count;    // length of the list built by the gather-select kernel
-  int pad2[19];
+  int pad2;
+  // running totals over all frames (folded in by begin_frame_kernel); used by the benchmark
+  unsigned long long tot_frames, tot_new_blocks, tot_visible_blocks, tot_updated_voxels, tot_carved_blocks;
+  unsigned long long pad3[4];
 };
 static_assert(sizeof(Counters) == 128, "Counters must stay one 128-byte line");
 constexpr size_t kCtrFrameOff = 16, kCtrFrameBytes = 32, kCtrGatherOff = 48;
@@ -125,17 +135,34 @@ struct ShardSpec {
   int rank, world, shift, halo;
 };
 
+// One hash-table slot: key and value side by side so a probe is a single 128-bit load.
+struct __align__(16) TableEntry {
+  uint64_t key;        // packed block coordinate or kEmptyKey
+  int val;             // pool index, kValFree or kValPending
+  int pad;
+};
+
+// One visible-list entry: everything the integrate kernel needs to find the slab (no meta[] hop).
+struct __align__(16) VisEntry {
+  uint64_t key;
+  int slot;
+  int idx_fresh;       // pool index | fresh << 31
+};
+
+// One pixel of the staged frame: 16 B, gathered with one 128-bit load per voxel.
+//   x = depth [m], y = rgb (r | g<<8 | b<<16 bits), z = ln ht - ln lt, w = w_new = (1 - depth/max_depth)*4
+typedef float4 FramePixel;
+
 // View of one grid's device memory; passed to kernels by value.
 struct GridView {
-  uint64_t* keys;      // [table_slots] packed block coordinate or kEmptyKey
-  int* vals;           // [table_slots] pool index, kValFree or kValPending
+  TableEntry* table;   // [table_slots]
   uint32_t slot_mask;  // table_slots - 1
   uint8_t* pool;       // [pool_blocks * kSlabBytes]
   BlockMeta* meta;     // [pool_blocks]
   int* heap;           // [pool_blocks] free-list stack
   int pool_blocks;
   Counters* ctr;
-  int* vis_list;       // [pool_blocks] pool indices selected for integration
+  VisEntry* vis_list;  // [pool_blocks] blocks selected for integration
   int* gather_list;    // [pool_blocks]
   ShardSpec shard;
 };
@@ -214,34 +241,52 @@ __device__ inline bool block_visible(S3 b, const Frame& f) {
 }
 
 // ---- lock-free open-addressed block table ------------------------------------------------------
-// keys[] only ever goes kEmptyKey -> key (64-bit CAS) and is never cleared: a carved block leaves
-// its key behind with vals[] == kValFree ("ghost"), so re-allocating the same coordinate next
-// frame reuses the slot and linear probing needs no tombstones.  vals[] goes
+// entry.key only ever goes kEmptyKey -> key (64-bit CAS) and is never cleared: a carved block
+// leaves its key behind with val == kValFree ("ghost"), so re-allocating the same coordinate next
+// frame reuses the slot and linear probing needs no tombstones.  val goes
 // kValFree -> kValPending -> pool index (allocation) and pool index -> kValFree (carving, in a
 // different kernel).  Lookups never run concurrently with inserts (separate launches).
+
+__device__ __forceinline__ TableEntry load_entry_nc(const TableEntry* e) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(e));
+  TableEntry r;
+  r.key = (uint64_t)(uint32_t)v.x | ((uint64_t)(uint32_t)v.y << 32);
+  r.val = v.z;
+  r.pad = 0;
+  return r;
+}
+__device__ __forceinline__ TableEntry load_entry_volatile(const TableEntry* e) {
+  int4 v;
+  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(e));
+  TableEntry r;
+  r.key = (uint64_t)(uint32_t)v.x | ((uint64_t)(uint32_t)v.y << 32);
+  r.val = v.z;
+  r.pad = 0;
+  return r;
+}
 
 // Read-only lookup: pool index of block `key`, or -1 (miss / ghost).
 __device__ inline int table_lookup(const GridView& g, uint64_t key, uint32_t home) {
   uint32_t s = home;
   for (uint32_t probe = 0; probe <= g.slot_mask; ++probe) {
-    const uint64_t k = __ldg((const unsigned long long*)&g.keys[s]);
-    if (k == key) {
-      const int v = __ldg(&g.vals[s]);
-      return v >= 0 ? v : -1;
-    }
-    if (k == kEmptyKey) return -1;
+    const TableEntry e = load_entry_nc(&g.table[s]);
+    if (e.key == key) return e.val >= 0 ? e.val : -1;
+    if (e.key == kEmptyKey) return -1;
     s = (s + 1) & g.slot_mask;
   }
   return -1;
 }
-// Same, through coherent loads (usable inside kernels that also insert).
-__device__ inline int table_find_slot_volatile(const GridView& g, uint64_t key, uint32_t home) {
-  uint32_t s = home;
+// Coherent probe (usable inside kernels that also insert), continuing from an already loaded
+// entry `e` of slot `s`.  Returns the slot holding `key` (and its value in *val) or -1.
+__device__ inline int table_find_slot_from(const GridView& g, uint64_t key, uint32_t s, TableEntry e, int* val) {
   for (uint32_t probe = 0; probe <= g.slot_mask; ++probe) {
-    const uint64_t k = *(volatile uint64_t*)&g.keys[s];
-    if (k == key) return (int)s;
-    if (k == kEmptyKey) return -1;
+    if (e.key == key) {
+      *val = e.val;
+      return (int)s;
+    }
+    if (e.key == kEmptyKey) return -1;
     s = (s + 1) & g.slot_mask;
+    e = load_entry_volatile(&g.table[s]);
   }
   return -1;
 }
@@ -249,9 +294,9 @@ __device__ inline int table_find_slot_volatile(const GridView& g, uint64_t key, 
 __device__ inline int table_find_or_claim_slot(const GridView& g, uint64_t key, uint32_t home) {
   uint32_t s = home;
   for (uint32_t probe = 0; probe <= g.slot_mask; ++probe) {
-    uint64_t k = *(volatile uint64_t*)&g.keys[s];
+    uint64_t k = *(volatile uint64_t*)&g.table[s].key;
     if (k == kEmptyKey) {
-      k = atomicCAS((unsigned long long*)&g.keys[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      k = atomicCAS((unsigned long long*)&g.table[s].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
       if (k == kEmptyKey) return (int)s;
     }
     if (k == key) return (int)s;
@@ -259,6 +304,10 @@ __device__ inline int table_find_or_claim_slot(const GridView& g, uint64_t key, 
   }
   return -1;
 }
+
+// p = 1 / (1 + exp(-logit)): logit -inf -> 0, +inf -> 1, 0 -> exactly 0.5, NaN -> NaN
+__device__ __forceinline__ float logit_to_prob(float l) { return 1.f / (1.f + expf(-l)); }
+__device__ __forceinline__ float prob_to_logit(float p) { return logf(p) - logf(1.f - p); }
 #endif  // __CUDACC__
 
 }  // namespace rsf

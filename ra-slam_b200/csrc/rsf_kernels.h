@@ -7,12 +7,14 @@
 namespace rsf {
 
 void launch_init_pool(const GridView& g, cudaStream_t s);
+void launch_begin_frame(const GridView& g, cudaStream_t s);
 void launch_allocate(const GridView& g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
-                     const float* lt, float4* frame, cudaStream_t s);
+                     const float* lt, FramePixel* frame, cudaStream_t s);
 void launch_select_visible(const GridView& g, const Frame& f, int sm_count, cudaStream_t s);
-void launch_integrate(const GridView& g, const Frame& f, const float4* frame, int sm_count, cudaStream_t s);
-void launch_raycast(const GridView& g, const Frame& f, float step_size, uchar4* rgba, uchar4* normal, float* depth,
-                    float* prob, cudaStream_t s);
+void launch_integrate(const GridView& g, const Frame& f, const FramePixel* frame, int sm_count, cudaStream_t s);
+size_t raycast_ranges_bytes(int W, int H);
+void launch_raycast(const GridView& g, const Frame& f, float step_size, unsigned* ranges, uchar4* rgba, uchar4* normal,
+                    float* depth, float* prob, int sm_count, cudaStream_t s);
 void launch_gather_select(const GridView& g, int mode, int owned_only, S3 lo, S3 hi, int sm_count, cudaStream_t s);
 void launch_download_rows(const GridView& g, float vs, int nblk, int ncol, float* rows, int sm_count, cudaStream_t s);
 void launch_export_blocks(const GridView& g, int nblk, short* coords, float* tsdf, uint32_t* rgbw, float* prob,

@@ -173,13 +173,13 @@ def render(scene: Scene, K: CameraIntrinsics, H: int, W: int, cam_T_world: SE3, 
     xs, ys = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
     dc = np.stack([(xs - K.cx) / K.fx, (ys - K.cy) / K.fy, np.ones_like(xs)], axis=-1)   # z component 1 => t = z-depth
     dw = dc @ R_wc.T
+    dw = np.where(np.abs(dw) < 1e-12, 1e-12, dw)      # axis-parallel rays: keep 1/dw finite
     with np.errstate(divide="ignore", invalid="ignore"):
         inv = 1.0 / dw
         # room: the camera is inside, take the nearest exit plane
         t_lo = (scene.room_min - eye) * inv
         t_hi = (scene.room_max - eye) * inv
         t_exit = np.where(dw > 0, t_hi, t_lo)
-        t_exit = np.where(np.isfinite(t_exit), t_exit, np.inf)
         axis_room = np.argmin(t_exit, axis=-1)
         t_room = np.min(t_exit, axis=-1)
         best = t_room.copy()
@@ -191,8 +191,6 @@ def render(scene: Scene, K: CameraIntrinsics, H: int, W: int, cam_T_world: SE3, 
             t1 = (bmax - eye) * inv
             tn = np.minimum(t0, t1)
             tf = np.maximum(t0, t1)
-            tn = np.where(np.isnan(tn), -np.inf, tn)
-            tf = np.where(np.isnan(tf), np.inf, tf)
             t_in = np.max(tn, axis=-1)
             t_out = np.min(tf, axis=-1)
             hit = (t_in < t_out) & (t_in > 1e-6) & (t_in < best)
