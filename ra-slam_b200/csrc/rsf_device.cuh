@@ -120,7 +120,8 @@ struct Counters {
   int pad2;
   // running totals over all frames (folded in by begin_frame_kernel); used by the benchmark
   unsigned long long tot_frames, tot_new_blocks, tot_visible_blocks, tot_updated_voxels, tot_carved_blocks;
-  unsigned long long pad3[4];
+  unsigned ray_work;   // next 8x4 pixel patch of the persistent raycast kernel
+  unsigned pad3[7];
 };
 static_assert(sizeof(Counters) == 128, "Counters must stay one 128-byte line");
 constexpr size_t kCtrFrameOff = 16, kCtrFrameBytes = 32, kCtrGatherOff = 48;

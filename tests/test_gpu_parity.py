@@ -135,6 +135,25 @@ def test_integrate_raycast_parity_config2(rsf, synth):
         assert r["rgba_max_abs"] <= 1 and r["normal_max_abs"] <= 1, r
 
 
+def test_raycast_parity_long_sequence(rsf, synth):
+    # long walk at low resolution: the map grows around and behind the camera (blocks straddling the
+    # camera plane, deep tile ranges, grazing rays); raycast must stay identical to marching every step
+    seq = synth.config2(n_frames=300, H=120, W=160)
+    at = (24, 74, 124, 174, 199)
+    g, o, rays = _run_both(rsf, seq, 200, raycast_at=at)
+    parity.assert_block_parity(parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks()))
+    for rg, ro in rays:
+        r = parity.compare_raycast(rg, ro, seq.voxel_size)
+        assert r["hit_mask_mismatch"] == 0, r
+        assert r["depth_max_vox"] <= 1e-3, r            # same IEEE op sequence: equal up to nothing
+        assert r["rgba_max_abs"] <= 1 and r["normal_max_abs"] <= 1, r
+    # a virtual camera far from the trajectory (TSDFSystem::Render with an arbitrary pose)
+    cam = rsf.CameraParams(synth.scaled(seq.K, 0.5, 0.5), 60, 80)
+    for pose in (seq.poses[3], seq.poses[150]):
+        r = parity.compare_raycast(g.RayCast(9.0, cam, pose), o.RayCast(9.0, cam, pose), seq.voxel_size)
+        assert r["hit_mask_mismatch"] == 0 and r["depth_max_vox"] <= 1e-3, r
+
+
 def test_integrate_parity_full_resolution(rsf, synth):
     # 640x480 at the reference's intrinsics; fewer frames so the oracle finishes in seconds
     seq = synth.config1(n_frames=100)
