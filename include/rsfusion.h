@@ -66,7 +66,8 @@ typedef struct rsf_options {
   int max_pixels;          /* largest H*W accepted; default 1920*1080 (reference)           */
   int shard_rank;          /* spatial sharding: this grid integrates only blocks it owns    */
   int shard_world;         /*   (+halo); world <= 1 disables sharding                       */
-  int shard_shift;         /*   owner = mix(block_pos >> shift) % world; default 1          */
+  int shard_shift;         /*   owner = mix(block_pos >> shift) % world; default 4 (16^3-   */
+                           /*   block super-bricks: ~1.4x replication with a 1-block halo)  */
   int shard_halo;          /*   redundant halo in blocks; default 1                         */
   void* stream;            /* optional external cudaStream_t; NULL = library-owned stream   */
   unsigned flags;          /* RSF_FLAG_* bits                                               */

@@ -159,7 +159,7 @@ struct Grid {
   std::unordered_map<uint64_t, std::unique_ptr<Block>> map;
   Stats stats{};
   // sharding
-  int shard_rank = 0, shard_world = 1, shard_shift = 1, shard_halo = 1;
+  int shard_rank = 0, shard_world = 1, shard_shift = 4, shard_halo = 1;
 
   bool wanted(S3 b) const {
     if (shard_world <= 1) return true;
@@ -435,6 +435,9 @@ void raycast(const Grid& g, float max_depth, int H, int W, const Intr& K, const 
           continue;
         }
         if (tp > 0 && tc <= 0 && tp - tc <= 2.0f) {
+          // sharded grids: only the owner of the block holding the crossing sample answers (halo
+          // copies are bit-identical but must stay silent so the min-depth merge takes one hit)
+          if (!g.owned(blk(gi))) break;
           const V3 p1 = p - sv;
           const float ac = pr.tri(p);
           const float ap = pr.tri(p1);

@@ -236,7 +236,7 @@ class TSDFGrid:
 
     def __init__(self, voxel_size: float, truncation: float, *, device: int = -1, pool_blocks: int = 0,
                  table_slots_log2: int = 0, max_pixels: int = 0, shard_rank: int = 0, shard_world: int = 1,
-                 shard_shift: int = 1, shard_halo: int = 1, stream: int | None = None):
+                 shard_shift: int = 4, shard_halo: int = 1, stream: int | None = None):
         self._lib = load_library()
         o = rsf_options()
         self._lib.rsf_default_options(C.byref(o))

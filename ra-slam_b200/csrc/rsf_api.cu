@@ -224,7 +224,7 @@ void rsf_default_options(rsf_options* o) {
   o->max_pixels = 1920 * 1080;       // MAX_IMG_SIZE, voxel_tsdf.cu:11-13
   o->shard_rank = 0;
   o->shard_world = 1;
-  o->shard_shift = 1;
+  o->shard_shift = 4;
   o->shard_halo = 1;
 }
 

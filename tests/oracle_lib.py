@@ -74,7 +74,7 @@ class OracleGrid:
             self.lib.ora_destroy(self.h)
             self.h = None
 
-    def set_shard(self, rank, world, shift=1, halo=1):
+    def set_shard(self, rank, world, shift=4, halo=1):
         self.lib.ora_set_shard(self.h, rank, world, shift, halo)
 
     def Integrate(self, rgb, depth, ht, lt, max_depth, intrinsics, cam_T_world):
