@@ -286,29 +286,54 @@ def run_native(args):
             pins.append(pa)
             row.append(pa.array)
         h_frames.append(tuple(row))
-    h_out = {}
-    for kname, shape, dt in (("rgba", (H, Wd, 4), np.uint8), ("normal", (H, Wd, 4), np.uint8), ("depth", (H, Wd), np.float32)):
-        pa = rsf.PinnedArray(shape, dt)
-        pins.append(pa)
-        h_out[kname] = pa.array
+    h_outs = []
+    for _ in range(2):      # double-buffered read-back targets
+        d = {}
+        for kname, shape, dt in (("rgba", (H, Wd, 4), np.uint8), ("normal", (H, Wd, 4), np.uint8), ("depth", (H, Wd), np.float32)):
+            pa = rsf.PinnedArray(shape, dt)
+            pins.append(pa)
+            d[kname] = pa.array
+        h_outs.append(d)
 
-    def step_e2e(i):
-        grid_e.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
-        grid_e.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_out)
-
+    # (a) pipelined: rsf_integrate_async + rsf_raycast_async, at most two frames in flight; every step's
+    #     H2D and D2H happen inside the timed region and every step's result is waited for
     for i in range(W):
-        step_e2e(i)
+        grid_e.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid_e.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
     barrier()
+    checksum = 0.0
     t0 = time.perf_counter()
+    prev = None
     for k in range(K):
-        step_e2e(W + k)
-    torch.cuda.synchronize()
+        i = W + k
+        grid_e.IntegrateAsync(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        t = grid_e.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k & 1])
+        if prev is not None:
+            grid_e.wait(prev)
+        prev = t
+    grid_e.wait(prev)
+    grid_e.synchronize()
     e2e_s = time.perf_counter() - t0
+    barrier()
+    checksum = float(h_outs[(K - 1) & 1]["depth"].sum())
+    grid_e.close()
+
+    # (b) blocking, reference-style calls (rsf_integrate + rsf_raycast return only when done)
+    grid_b = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank)
+    Kb = min(K, 100)
+    for i in range(W):
+        grid_b.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+    grid_b.synchronize()
+    t0 = time.perf_counter()
+    for k in range(Kb):
+        i = W + k
+        grid_b.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid_b.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
+    e2e_blocking_s = (time.perf_counter() - t0) / Kb
+    grid_b.close()
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
-    checksum = float(h_out["depth"].sum())
-    grid_e.close()
 
     # ---------------- max over ranks ---------------------------------------------------------------
     if dist is not None:
@@ -342,7 +367,10 @@ def run_native(args):
                    "parallelism": f"replicas x{world} (independent sequences, no collective)" if world > 1 else "1 grid"},
         "value_warm_l2": world * K / (warm_ms * 1e-3),
         "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 12 * P,
-                "ms_per_step": 1e3 * e2e_s / K, "api": "rsf_integrate + rsf_raycast (blocking, pinned host buffers)",
+                "ms_per_step": 1e3 * e2e_s / K,
+                "api": "rsf_integrate_async + rsf_raycast_async + rsf_wait (3-stream pipeline, <= 2 frames in flight, "
+                       "pinned host buffers)",
+                "blocking_value": world / e2e_blocking_s, "blocking_api": "rsf_integrate + rsf_raycast",
                 "checksum": checksum},
         # per frame: begin_frame, allocate, select_visible, integrate, tile_range, raycast
         "gpu_launches": int(sum(v[1] for v in prof.values()) + int_n + prof["raycast"][1]),

@@ -97,6 +97,15 @@ RSF_API int rsf_destroy(rsf_grid_t g);
  * ht/lt: H*W f32 high-/low-touch probabilities (CV_32FC1).  Host buffers; blocking. */
 RSF_API int rsf_integrate(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
                   int H, int W, float max_depth, const float K[4], const float pose[7]);
+/* Pipelined form: returns as soon as the copies and kernels are enqueued (H2D on a copy stream,
+ * double-buffered, overlapping the kernels of the previous frame).  The host buffers must stay
+ * valid and unchanged until a later rsf_synchronize / rsf_wait on this grid returns; pass
+ * page-locked memory (rsf_host_alloc) for true asynchronous DMA.  Device-side errors (pool or table
+ * exhaustion) surface at the next rsf_synchronize / blocking call.  This is the path
+ * TSDFSystem's worker thread (modules/tsdf_module.cc:88-115) maps onto. */
+RSF_API int rsf_integrate_async(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht,
+                                const float* lt, int H, int W, float max_depth, const float K[4],
+                                const float pose[7]);
 /* Same with the frame already resident in device memory; asynchronous on the grid's stream. */
 RSF_API int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht,
                          const float* lt, int H, int W, float max_depth, const float K[4],
@@ -108,6 +117,13 @@ RSF_API int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* 
  * Host buffers; blocking. */
 RSF_API int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
                 uint8_t* rgba, uint8_t* normal, float* depth, float* prob);
+/* Pipelined form: kernels on the grid's stream, read-back on a separate D2H stream, double-buffered.
+ * *ticket identifies the read-back; the host outputs are valid after rsf_wait(g, ticket) (or
+ * rsf_synchronize).  At most two read-backs are in flight: a third call reuses the first ticket's
+ * staging and implicitly orders after it. */
+RSF_API int rsf_raycast_async(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
+                              uint8_t* rgba, uint8_t* normal, float* depth, float* prob, int* ticket);
+RSF_API int rsf_wait(rsf_grid_t g, int ticket);
 /* Device outputs; asynchronous on the grid's stream. */
 RSF_API int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
                        uint8_t* rgba, uint8_t* normal, float* depth, float* prob);

@@ -59,6 +59,9 @@ ABI = {
     "rsf_create": (C.c_int, [C.POINTER(rsf_options), C.POINTER(_P)]),
     "rsf_destroy": (C.c_int, [_P]),
     "rsf_integrate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
+    "rsf_integrate_async": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
+    "rsf_raycast_async": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P, C.POINTER(C.c_int)]),
+    "rsf_wait": (C.c_int, [_P, C.c_int]),
     "rsf_integrate_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
     "rsf_raycast": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
@@ -312,6 +315,29 @@ class TSDFGrid:
 
     def synchronize(self):
         _check(self._lib.rsf_synchronize(self._h))
+
+    # -- pipelined host path (rsf_integrate_async / rsf_raycast_async / rsf_wait) ----------------
+    def IntegrateAsync(self, img_rgb, img_depth, img_ht, img_lt, max_depth: float, intrinsics: CameraIntrinsics,
+                       cam_T_world: SE3):
+        """Enqueue only.  The (ideally pinned) numpy buffers must stay alive and unchanged until
+        `synchronize()` / `wait()` returns."""
+        H, W = img_depth.shape
+        K, pose = intrinsics.as_array(), cam_T_world.as_array()
+        _check(self._lib.rsf_integrate_async(self._h, img_rgb.ctypes.data, img_depth.ctypes.data, img_ht.ctypes.data,
+                                             img_lt.ctypes.data, H, W, max_depth, _fptr(K), _fptr(pose)))
+
+    def RayCastAsync(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3, out: dict) -> int:
+        """Enqueue raycast + read-back into the numpy arrays of `out`; returns a ticket for `wait`."""
+        K, pose = virtual_cam.intrinsics.as_array(), cam_T_world.as_array()
+        ptr = {k: (out[k].ctypes.data if k in out else None) for k in ("rgba", "normal", "depth", "prob")}
+        t = C.c_int(0)
+        _check(self._lib.rsf_raycast_async(self._h, max_depth, virtual_cam.img_h, virtual_cam.img_w, _fptr(K),
+                                           _fptr(pose), ptr["rgba"], ptr["normal"], ptr["depth"], ptr["prob"],
+                                           C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        _check(self._lib.rsf_wait(self._h, ticket))
 
     # -- exports --------------------------------------------------------------------------------
     def _gather(self, fn, ncol, *pre):

@@ -62,13 +62,26 @@ struct rsf_grid_s {
   GridView view{};
   size_t table_slots = 0;
   size_t max_pixels = 0;
-  // frame staging (device)
-  uint8_t* d_rgb = nullptr;
-  float *d_depth = nullptr, *d_ht = nullptr, *d_lt = nullptr;
-  float4* d_frame = nullptr;
-  // raycast outputs (device)
-  uchar4 *d_rgba = nullptr, *d_normal = nullptr;
-  float *d_rdepth = nullptr, *d_rprob = nullptr;
+  // Host entry points run a 3-stage pipeline: H2D on `s_h2d` -> kernels on `stream` -> D2H on
+  // `s_d2h`, chained with events and double-buffered, so the copy of frame k+1 and the read-back
+  // of frame k-1 overlap the kernels of frame k (the reference copies, computes and reads back
+  // serially on one stream, voxel_tsdf.cu:433-451).
+  static constexpr int kSlots = 2;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  struct InSlot {
+    uint8_t* rgb = nullptr;
+    float *depth = nullptr, *ht = nullptr, *lt = nullptr;
+    cudaEvent_t ready = nullptr;   // H2D done (recorded on s_h2d)
+    cudaEvent_t free_ = nullptr;   // allocate kernel has consumed the slot (recorded on stream)
+  } in[kSlots];
+  struct OutSlot {
+    uchar4 *rgba = nullptr, *normal = nullptr;
+    float *depth = nullptr, *prob = nullptr;
+    cudaEvent_t ready = nullptr;   // raycast done (recorded on stream)
+    cudaEvent_t done = nullptr;    // D2H done (recorded on s_d2h)
+  } out[kSlots];
+  unsigned in_next = 0, out_next = 0;
+  float4* d_frame = nullptr;       // staged frame records (written by allocate, read by integrate)
   unsigned* d_ranges = nullptr;   // per-tile depth ranges of the raycast pre-pass
   // pinned mirror of the device counters
   Counters* h_ctr = nullptr;
@@ -147,12 +160,14 @@ struct ProfScope {
 };
 
 int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
-                      const float* lt) {
+                      const float* lt, cudaEvent_t inputs_consumed = nullptr) {
   launch_begin_frame(g->view, g->stream);
   {
     ProfScope p(g, RSF_PROF_ALLOCATE);
     launch_allocate(g->view, f, rgb, depth, ht, lt, g->d_frame, g->stream);
   }
+  // the allocate kernel is the only reader of the raw images (it stages them into d_frame)
+  if (inputs_consumed) RSF_CUDA(cudaEventRecord(inputs_consumed, g->stream));
   {
     ProfScope p(g, RSF_PROF_SELECT);
     launch_select_visible(g->view, f, g->sm_count, g->stream);
@@ -292,15 +307,25 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   A((void**)&v.vis_list, (size_t)o.pool_blocks * sizeof(VisEntry));
   A((void**)&v.gather_list, (size_t)o.pool_blocks * sizeof(int));
   A((void**)&v.ctr, sizeof(Counters));
-  A((void**)&g->d_rgb, P * 3);
-  A((void**)&g->d_depth, P * sizeof(float));
-  A((void**)&g->d_ht, P * sizeof(float));
-  A((void**)&g->d_lt, P * sizeof(float));
   A((void**)&g->d_frame, P * sizeof(float4));
-  A((void**)&g->d_rgba, P * sizeof(uchar4));
-  A((void**)&g->d_normal, P * sizeof(uchar4));
-  A((void**)&g->d_rdepth, P * sizeof(float));
-  A((void**)&g->d_rprob, P * sizeof(float));
+  for (auto& sl : g->in) {
+    A((void**)&sl.rgb, P * 3);
+    A((void**)&sl.depth, P * sizeof(float));
+    A((void**)&sl.ht, P * sizeof(float));
+    A((void**)&sl.lt, P * sizeof(float));
+    ok = ok && cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&sl.free_, cudaEventDisableTiming) == cudaSuccess;
+  }
+  for (auto& sl : g->out) {
+    A((void**)&sl.rgba, P * sizeof(uchar4));
+    A((void**)&sl.normal, P * sizeof(uchar4));
+    A((void**)&sl.depth, P * sizeof(float));
+    A((void**)&sl.prob, P * sizeof(float));
+    ok = ok && cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
   A((void**)&g->d_ranges, (P / 256 + 4096) * 2 * sizeof(unsigned) + 64);
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   if (ok) {
@@ -323,10 +348,27 @@ int rsf_destroy(rsf_grid_t g) {
   DeviceGuard dg(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   GridView& v = g->view;
-  void* ptrs[] = {v.table,  v.pool,     v.meta,    v.heap,    v.vis_list, v.gather_list, v.ctr,     g->d_rgb,
-                  g->d_depth, g->d_ht,  g->d_lt,    g->d_frame, g->d_rgba, g->d_normal, g->d_rdepth,  g->d_rprob, g->d_ranges};
+  if (g->s_h2d) cudaStreamSynchronize(g->s_h2d);
+  if (g->s_d2h) cudaStreamSynchronize(g->s_d2h);
+  void* ptrs[] = {v.table, v.pool, v.meta, v.heap, v.vis_list, v.gather_list, v.ctr, g->d_frame, g->d_ranges};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& sl : g->in) {
+    void* q[] = {sl.rgb, sl.depth, sl.ht, sl.lt};
+    for (void* p : q)
+      if (p) cudaFree(p);
+    if (sl.ready) cudaEventDestroy(sl.ready);
+    if (sl.free_) cudaEventDestroy(sl.free_);
+  }
+  for (auto& sl : g->out) {
+    void* q[] = {sl.rgba, sl.normal, sl.depth, sl.prob};
+    for (void* p : q)
+      if (p) cudaFree(p);
+    if (sl.ready) cudaEventDestroy(sl.ready);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
+  if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
   for (auto& v : g->prof_events)
     for (auto& e : v) {
@@ -338,19 +380,30 @@ int rsf_destroy(rsf_grid_t g) {
   return RSF_OK;
 }
 
-int rsf_integrate(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H, int W,
-                  float max_depth, const float K[4], const float pose[7]) {
+int rsf_integrate_async(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H,
+                        int W, float max_depth, const float K[4], const float pose[7]) {
   if (int rc = check_grid(g)) return rc;
   if (!rgb || !depth || !ht || !lt) return fail(RSF_ERR_INVALID, "rgb / depth / ht / lt must not be NULL");
   Frame f;
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
   const size_t P = (size_t)H * W;
-  RSF_CUDA(cudaMemcpyAsync(g->d_depth, depth, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
-  RSF_CUDA(cudaMemcpyAsync(g->d_rgb, rgb, P * 3, cudaMemcpyHostToDevice, g->stream));
-  RSF_CUDA(cudaMemcpyAsync(g->d_ht, ht, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
-  RSF_CUDA(cudaMemcpyAsync(g->d_lt, lt, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
-  if (int rc = enqueue_integrate(g, f, g->d_rgb, g->d_depth, g->d_ht, g->d_lt)) return rc;
+  auto& sl = g->in[g->in_next++ % rsf_grid_s::kSlots];
+  RSF_CUDA(cudaStreamWaitEvent(g->s_h2d, sl.free_, 0));       // previous user of this slot has consumed it
+  RSF_CUDA(cudaMemcpyAsync(sl.depth, depth, P * sizeof(float), cudaMemcpyHostToDevice, g->s_h2d));
+  RSF_CUDA(cudaMemcpyAsync(sl.rgb, rgb, P * 3, cudaMemcpyHostToDevice, g->s_h2d));
+  RSF_CUDA(cudaMemcpyAsync(sl.ht, ht, P * sizeof(float), cudaMemcpyHostToDevice, g->s_h2d));
+  RSF_CUDA(cudaMemcpyAsync(sl.lt, lt, P * sizeof(float), cudaMemcpyHostToDevice, g->s_h2d));
+  RSF_CUDA(cudaEventRecord(sl.ready, g->s_h2d));
+  RSF_CUDA(cudaStreamWaitEvent(g->stream, sl.ready, 0));
+  if (int rc = enqueue_integrate(g, f, sl.rgb, sl.depth, sl.ht, sl.lt, sl.free_)) return rc;
+  return RSF_OK;
+}
+
+int rsf_integrate(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H, int W,
+                  float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = rsf_integrate_async(g, rgb, depth, ht, lt, H, W, max_depth, K, pose)) return rc;
+  DeviceGuard dg(g->device);
   return sync_counters(g);
 }
 
@@ -380,32 +433,55 @@ int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float 
   return RSF_OK;
 }
 
-int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,
-                uint8_t* normal, float* depth, float* prob) {
+int rsf_raycast_async(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,
+                      uint8_t* normal, float* depth, float* prob, int* ticket) {
   if (int rc = check_grid(g)) return rc;
   Frame f;
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
+  const int slot = (int)(g->out_next++ % rsf_grid_s::kSlots);
+  auto& sl = g->out[slot];
+  RSF_CUDA(cudaStreamWaitEvent(g->stream, sl.done, 0));       // read-back of the previous user has finished
   {
     ProfScope p(g, RSF_PROF_RAYCAST);
-    launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, rgba ? g->d_rgba : nullptr,
-                   normal ? g->d_normal : nullptr, depth ? g->d_rdepth : nullptr, prob ? g->d_rprob : nullptr,
-                   g->sm_count, g->stream);
+    launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, rgba ? sl.rgba : nullptr, normal ? sl.normal : nullptr,
+                   depth ? sl.depth : nullptr, prob ? sl.prob : nullptr, g->sm_count, g->stream);
   }
   RSF_CUDA(cudaGetLastError());
+  RSF_CUDA(cudaEventRecord(sl.ready, g->stream));
+  RSF_CUDA(cudaStreamWaitEvent(g->s_d2h, sl.ready, 0));
   const size_t P = (size_t)H * W;
-  if (rgba) RSF_CUDA(cudaMemcpyAsync(rgba, g->d_rgba, P * 4, cudaMemcpyDeviceToHost, g->stream));
-  if (normal) RSF_CUDA(cudaMemcpyAsync(normal, g->d_normal, P * 4, cudaMemcpyDeviceToHost, g->stream));
-  if (depth) RSF_CUDA(cudaMemcpyAsync(depth, g->d_rdepth, P * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
-  if (prob) RSF_CUDA(cudaMemcpyAsync(prob, g->d_rprob, P * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
-  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  if (rgba) RSF_CUDA(cudaMemcpyAsync(rgba, sl.rgba, P * 4, cudaMemcpyDeviceToHost, g->s_d2h));
+  if (normal) RSF_CUDA(cudaMemcpyAsync(normal, sl.normal, P * 4, cudaMemcpyDeviceToHost, g->s_d2h));
+  if (depth) RSF_CUDA(cudaMemcpyAsync(depth, sl.depth, P * sizeof(float), cudaMemcpyDeviceToHost, g->s_d2h));
+  if (prob) RSF_CUDA(cudaMemcpyAsync(prob, sl.prob, P * sizeof(float), cudaMemcpyDeviceToHost, g->s_d2h));
+  RSF_CUDA(cudaEventRecord(sl.done, g->s_d2h));
+  if (ticket) *ticket = slot;
   return RSF_OK;
+}
+
+int rsf_wait(rsf_grid_t g, int ticket) {
+  if (int rc = check_grid(g)) return rc;
+  if (ticket < 0 || ticket >= rsf_grid_s::kSlots) return fail(RSF_ERR_INVALID, "bad ticket %d", ticket);
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaEventSynchronize(g->out[ticket].done));
+  return RSF_OK;
+}
+
+int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,
+                uint8_t* normal, float* depth, float* prob) {
+  int ticket = 0;
+  if (int rc = rsf_raycast_async(g, max_depth, H, W, K, pose, rgba, normal, depth, prob, &ticket)) return rc;
+  return rsf_wait(g, ticket);
 }
 
 int rsf_synchronize(rsf_grid_t g) {
   if (int rc = check_grid(g)) return rc;
   DeviceGuard dg(g->device);
-  return sync_counters(g);
+  RSF_CUDA(cudaStreamSynchronize(g->s_h2d));
+  if (int rc = sync_counters(g)) return rc;
+  RSF_CUDA(cudaStreamSynchronize(g->s_d2h));
+  return RSF_OK;
 }
 
 int rsf_num_active_blocks(rsf_grid_t g, int64_t* n) {

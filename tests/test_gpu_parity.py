@@ -224,3 +224,43 @@ def test_device_pointer_path_matches_host_path(rsf, synth):
     g2.synchronize()
     assert np.array_equal(out["rgba"].cpu().numpy(), r1["rgba"])
     assert np.array_equal(out["depth"].cpu().numpy(), r1["depth"])
+
+
+def test_pipelined_host_path_matches_blocking(rsf, synth):
+    # rsf_integrate_async / rsf_raycast_async / rsf_wait (3-stream pipeline, 2 frames in flight) must
+    # give exactly what the blocking calls give
+    seq = synth.config2(n_frames=300, H=120, W=160)
+    cam = rsf.CameraParams(seq.K, seq.H, seq.W)
+    n = 24
+    g1 = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    g2 = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    frames = [seq.frame(i) for i in range(n)]
+    pins, hf = [], []
+    for fr in frames:
+        row = []
+        for a in fr:
+            pa = rsf.PinnedArray(a.shape, a.dtype)
+            pa.array[...] = a
+            pins.append(pa)
+            row.append(pa.array)
+        hf.append(row)
+    outs = [{"rgba": np.zeros((seq.H, seq.W, 4), np.uint8), "depth": np.zeros((seq.H, seq.W), np.float32),
+             "prob": np.zeros((seq.H, seq.W), np.float32)} for _ in range(n)]
+    ref = []
+    tickets = []
+    for i in range(n):
+        g1.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
+        ref.append(g1.RayCast(8.0, cam, seq.poses[i], outputs=("rgba", "depth", "prob")))
+        g2.IntegrateAsync(*hf[i], seq.max_depth, seq.K, seq.poses[i])
+        tickets.append(g2.RayCastAsync(8.0, cam, seq.poses[i], outs[i]))
+        if i >= 1:
+            g2.wait(tickets[i - 1])
+            for k in ("rgba", "depth", "prob"):
+                assert np.array_equal(outs[i - 1][k], ref[i - 1][k], equal_nan=True), (i - 1, k)
+    g2.synchronize()
+    for k in ("rgba", "depth", "prob"):
+        assert np.array_equal(outs[-1][k], ref[-1][k], equal_nan=True)
+    for x, y in zip(g1.ExportBlocks(), g2.ExportBlocks()):
+        assert np.array_equal(x, y, equal_nan=True)
+    for pa in pins:
+        pa.free()
