@@ -264,3 +264,58 @@ def test_pipelined_host_path_matches_blocking(rsf, synth):
         assert np.array_equal(x, y, equal_nan=True)
     for pa in pins:
         pa.free()
+
+
+def test_cpp_adapter_tsdf_system(rsf, synth, tmp_path):
+    """The header-only C++ adapter (rsfusion::TSDFSystem, the reference's class surface) driven like
+    main/offline_eval.cc, against the ctypes path on the same frames."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "cpp", "adapter_main")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    seq = synth.config2(n_frames=300, H=120, W=160)
+    n = 30
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    rng = np.random.default_rng(5)
+    mats = []
+    for _ in range(2):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        mats.append(rsf.SE3(q, rng.normal(size=3)).matrix().astype(np.float32))
+    fpath = tmp_path / "frames.bin"
+    with open(fpath, "wb") as f:
+        f.write(np.array([n, seq.H, seq.W], np.int32).tobytes())
+        f.write(seq.K.as_array().tobytes())
+        f.write(np.array([seq.voxel_size, seq.truncation, seq.max_depth], np.float32).tobytes())
+        for i in range(n):
+            fr = seq.frame(i)
+            g.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+            f.write(seq.poses[i].as_array().tobytes())
+            for a in fr:
+                f.write(np.ascontiguousarray(a).tobytes())
+        f.write(np.stack(mats).tobytes())
+    out = subprocess.check_output([exe, str(fpath), str(tmp_path / "out")], text=True)
+    assert "type_check ok" in out
+    assert f"active_blocks {g.NumActiveBlock()} " in out
+    ref = g.RayCast(seq.max_depth * 2, rsf.CameraParams(seq.K, seq.H, seq.W), seq.poses[n - 1])
+    P = seq.H * seq.W
+    assert np.array_equal(np.fromfile(tmp_path / "out.rgba", np.uint8), ref["rgba"].ravel())
+    assert np.array_equal(np.fromfile(tmp_path / "out.normal", np.uint8), ref["normal"].ravel())
+    assert np.array_equal(np.fromfile(tmp_path / "out.depth", np.float32), ref["depth"].ravel())
+
+    def canon(rows):
+        key = np.round(rows[:, :3] / seq.voxel_size).astype(np.int64)
+        return rows[np.lexsort((key[:, 0], key[:, 1], key[:, 2]))]
+
+    rows = np.fromfile(tmp_path / "out.tsdf", np.float32).reshape(-1, 5)     # TSDFSystem::DownloadAll format
+    assert np.array_equal(canon(rows), canon(g.GatherValidSemantic()))
+    q = np.fromfile(tmp_path / "out.query", np.float32).reshape(-1, 4)
+    assert len(q) > 0 and np.array_equal(canon(q), canon(g.GatherVoxels(rsf.BoundingCube(0.0, 2.5, 0.0, 4.0, 0.0, 1.5))))
+    # SE3(Matrix4f) / operator* / Inverse against the Python mirror of the same Eigen algorithm
+    se3 = np.fromfile(tmp_path / "out.se3", np.float32).reshape(4, 7)
+    A, B = rsf.SE3.from_matrix(mats[0]), rsf.SE3.from_matrix(mats[1])
+    assert np.array_equal(se3[0], A.as_array()) and np.array_equal(se3[1], B.as_array())
+    assert np.allclose(rsf.SE3(se3[2][:4], se3[2][4:]).matrix(), A.matrix() @ B.matrix(), atol=1e-5)
+    assert np.allclose(rsf.SE3(se3[3][:4], se3[3][4:]).matrix(), np.linalg.inv(A.matrix()), atol=1e-5)
