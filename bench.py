@@ -38,6 +38,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("RSF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
 
 METRIC = "frames/s integrate+raycast 640x480 semantic (TUM fr1-shaped)"
 UNIT = "frames/s"
@@ -190,7 +191,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def run_native(args):
@@ -390,7 +391,7 @@ def run_native(args):
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{s} frames after {W} map-building frames, oracle/rsf_oracle.cpp "
                                           f"(multithreaded restatement; the reference has no CPU path)", **br}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -276,3 +276,58 @@ def config5(n_frames: int = 200, H: int = 480, W: int = 640) -> Sequence:
     sc = building_scene(seed=3)
     K = TUM_FR1 if (H, W) == (480, 640) else scaled(TUM_FR1, W / 640.0, H / 480.0)
     return Sequence("building-5mm", K, H, W, walk_trajectory(sc, n_frames, seed=3), sc, 0.005, 0.03, 8.0)
+
+
+def render_torch(scene: Scene, K: CameraIntrinsics, H: int, W: int, cam_T_world: SE3, device, *,
+                 depth_factor: float | None = None, max_range: float = 60.0):
+    """Same image formation as :func:`render`, evaluated with torch on `device` (float64).  Used by the
+    large-scene benchmark where the building has ~70 boxes and numpy would take seconds per frame.
+    Returns torch tensors (rgb u8 HxWx3, depth f32, ht f32, lt f32) on `device`."""
+    import torch
+    f64 = torch.float64
+    R_cw = torch.as_tensor(cam_T_world.rotation_matrix(), dtype=f64, device=device)
+    t_cw = torch.as_tensor(cam_T_world.t.astype(np.float64), dtype=f64, device=device)
+    R_wc = R_cw.T
+    eye = -(R_wc @ t_cw)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=f64, device=device), torch.arange(W, dtype=f64, device=device), indexing="ij")
+    dc = torch.stack([(xs - K.cx) / K.fx, (ys - K.cy) / K.fy, torch.ones_like(xs)], dim=-1)
+    dw = dc @ R_wc.T
+    dw = torch.where(dw.abs() < 1e-12, torch.full_like(dw, 1e-12), dw)
+    inv = 1.0 / dw
+    rmin = torch.as_tensor(scene.room_min, dtype=f64, device=device)
+    rmax = torch.as_tensor(scene.room_max, dtype=f64, device=device)
+    t_exit = torch.where(dw > 0, (rmax - eye) * inv, (rmin - eye) * inv)
+    best, axis = t_exit.min(dim=-1)
+    side_hi = torch.gather(dw > 0, -1, axis[..., None])[..., 0]
+    kind = torch.zeros((H, W), dtype=torch.int32, device=device)
+    if scene.boxes:
+        bmin = torch.as_tensor(np.stack([b[0] for b in scene.boxes]), dtype=f64, device=device)   # (B,3)
+        bmax = torch.as_tensor(np.stack([b[1] for b in scene.boxes]), dtype=f64, device=device)
+        for s in range(0, len(scene.boxes), 16):
+            t0 = (bmin[s:s + 16, None, None, :] - eye) * inv
+            t1 = (bmax[s:s + 16, None, None, :] - eye) * inv
+            tn, tf = torch.minimum(t0, t1), torch.maximum(t0, t1)
+            t_in, ax_in = tn.max(dim=-1)
+            t_out = tf.min(dim=-1).values
+            t_in = torch.where((t_in < t_out) & (t_in > 1e-6), t_in, torch.full_like(t_in, float("inf")))
+            tb, ib = t_in.min(dim=0)
+            axb = torch.gather(ax_in, 0, ib[None])[0]
+            hit = tb < best
+            best = torch.where(hit, tb, best)
+            kind = torch.where(hit, torch.ones_like(kind), kind)
+            axis = torch.where(hit, axb, axis)
+    depth = torch.where(best < max_range, best, torch.zeros_like(best))
+    pw = eye + dw * best[..., None]
+    cell = torch.floor((pw + 1e-4) / 0.25).to(torch.int64)
+    chk = (cell.sum(dim=-1) & 1).bool()
+    base = torch.where(chk[..., None], torch.tensor([200, 60, 60], device=device), torch.tensor([60, 80, 200], device=device))
+    shade = 40 * (axis[..., None] == torch.arange(3, device=device)).sum(dim=-1)
+    rgb = (base + shade[..., None] - 20).clamp(0, 255).to(torch.uint8)
+    touch = (kind == 1) | ((kind == 0) & (axis == scene.touch_wall_axis) & side_hi)
+    ht = torch.where(touch, 0.9, 0.1).to(torch.float32)
+    lt = (1.0 - ht).to(torch.float32)
+    depth = depth.to(torch.float32)
+    if depth_factor:
+        q = torch.round(depth.to(f64) * depth_factor).clamp(0, 65535)
+        depth = (q.to(torch.float32) * np.float32(1.0 / depth_factor)).to(torch.float32)
+    return rgb.contiguous(), depth.contiguous(), ht.contiguous(), lt.contiguous()
