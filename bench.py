@@ -2,7 +2,8 @@
 """bench.py -- frames/s of the TSDF fusion hot path (integrate + raycast per frame) on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own TSDFGrid (oracle/_ref, CUDA;
+                                                             # it has no CPU path), else the CPU oracle port
 
 A step = one frame of the workload: TSDFGrid::Integrate of a 640x480 RGB + depth + ht/lt frame
 followed by TSDFGrid::RayCast from the same pose at max_depth*2 (TSDFSystem::Render,
@@ -164,32 +165,101 @@ def cpu_oracle_fps(seq, frames, warm, sample, threads=0):
     return n / dt, {"integrate_ms": 1e3 * ti / n, "raycast_ms": 1e3 * tr / n}
 
 
+def reference_gpu_fps(seq, frames, W, K, pinned):
+    """The reference's OWN TSDFGrid (oracle/_ref/libref_tsdf.so: unmodified utils/tsdf/*.cu built against
+    oracle/ref_shim) through its public blocking API: Integrate(host images) + RayCast per frame, as
+    TSDFSystem does (modules/tsdf_module.cc:45-49, 88-115).  Wall clock; both calls end with a stream sync."""
+    import torch
+    import ref_lib
+    g = ref_lib.RefGrid(seq.voxel_size, seq.truncation)
+    Kx = seq.K.as_array()
+    hold = []
+    ptrs = []
+    for fr in frames:
+        row = []
+        for a in fr:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if pinned:
+                t = t.pin_memory()
+            hold.append(t)
+            row.append(t.data_ptr())
+        ptrs.append(row)
+    poses = [p.as_array() for p in seq.poses]
+    rmax = seq.max_depth * 2
+    for i in range(W):
+        g.integrate_raw(*ptrs[i], seq.H, seq.W, seq.max_depth, Kx, poses[i])
+        g.raycast_raw(rmax, seq.H, seq.W, Kx, poses[i])
+    torch.cuda.synchronize()
+    ti = tr = 0.0
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        a = time.perf_counter()
+        g.integrate_raw(*ptrs[i], seq.H, seq.W, seq.max_depth, Kx, poses[i])
+        b = time.perf_counter()
+        g.raycast_raw(rmax, seq.H, seq.W, Kx, poses[i])
+        c = time.perf_counter()
+        ti += b - a
+        tr += c - b
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n_active = g.NumActiveBlock()
+    del g
+    return K / dt, {"integrate_ms": 1e3 * ti / K, "raycast_ms": 1e3 * tr / K, "active_blocks": n_active}
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm on the box's host cores (CPU oracle port; the
-    reference has no CPU path and does not build offline)."""
+    """--impl reference.  The reference has NO CPU implementation of this path (it is CUDA-only), so its "own
+    implementation" is its CUDA TSDFGrid: when oracle/_ref/libref_tsdf.so exists (built in the development
+    container from the reference's unmodified sources, see oracle/Makefile) and a GPU is visible, that is what
+    is timed, through the reference's blocking public API with host images.  Otherwise the multithreaded CPU
+    oracle port is timed on the host cores."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    # bounded sample: each step is one frame; cap the run to a few minutes of CPU work
-    K = min(K, 60)
-    W = min(W, 20)
-    seq = make_sequence(args, 0, W + K)
-    frames = render_frames(seq, W + K)
-    cores = os.cpu_count() or 1
-    fps, br = cpu_oracle_fps(seq, frames, W, K, cores)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_lib
+    use_ref = ref_lib.available()
+    if use_ref:
+        try:
+            import torch
+            use_ref = torch.cuda.is_available()
+        except Exception:
+            use_ref = False
+    cfg = {"workload": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame"}
+    if use_ref:
+        seq = make_sequence(args, 0, W + K)
+        frames = render_frames(seq, W + K)
+        fps_pg, br_pg = reference_gpu_fps(seq, frames, W, K, pinned=False)
+        fps_pin, br_pin = reference_gpu_fps(seq, frames, W, K, pinned=True)
+        fps, br = (fps_pin, br_pin) if fps_pin >= fps_pg else (fps_pg, br_pg)
+        P = seq.H * seq.W
+        cpu = {"value": fps, "unit": UNIT, "cores": 1, "kind": "reference",
+               "device": "B200: the reference's own CUDA kernels (it has no CPU path); 1 host thread drives them",
+               "sample": f"{K} frames after {W} map-building frames; unmodified utils/tsdf/*.cu compiled for sm_100a "
+                         "against oracle/ref_shim (Eigen/OpenCV/GL stand-ins), TSDFGrid::Integrate + RayCast, blocking; "
+                         "value = the faster of pageable (stock cv::Mat) and pinned host images",
+               "pageable_inputs_value": fps_pg, "pinned_inputs_value": fps_pin, **br}
+        e2e = {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 0}
+        cfg["parallelism"] = "1 grid, reference CUDA build"
+    else:
+        # bounded sample: each step is one frame; cap the run to a few minutes of CPU work
+        K = min(K, 60)
+        W = min(W, 20)
+        seq = make_sequence(args, 0, W + K)
+        frames = render_frames(seq, W + K)
+        cores = os.cpu_count() or 1
+        fps, br = cpu_oracle_fps(seq, frames, W, K, cores)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{K} frames after {W} map-building frames, oracle/rsf_oracle.cpp, {cores} threads", **br}
+        e2e = {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        cfg["parallelism"] = "host threads"
+    cfg.update({"height": seq.H, "width": seq.W, "voxel_size": seq.voxel_size, "truncation": seq.truncation,
+                "max_depth": seq.max_depth, "raycast_max_depth": seq.max_depth * 2})
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame", "height": seq.H,
-                   "width": seq.W, "voxel_size": seq.voxel_size, "truncation": seq.truncation,
-                   "max_depth": seq.max_depth, "parallelism": "host threads"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{K} frames after {W} map-building frames, oracle/rsf_oracle.cpp, {cores} threads",
-                         **br},
-        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 

@@ -115,7 +115,7 @@ class SE3 {
   static SE3<T> Identity() { return SE3<T>(); }
 
   SE3<T> Inverse() const {
-    const T n2 = ((q_[1] * q_[1] + q_[2] * q_[2]) + q_[3] * q_[3]) + q_[0] * q_[0];
+    const T n2 = (q_[1] * q_[1] + q_[2] * q_[2]) + (q_[3] * q_[3] + q_[0] * q_[0]);  // Eigen redux order (x,y | z,w)
     std::array<T, 4> qi{0, 0, 0, 0};
     if (n2 > T(0)) qi = {q_[0] / n2, -q_[1] / n2, -q_[2] / n2, -q_[3] / n2};
     return SE3<T>(qi, rotate(qi, {-t_[0], -t_[1], -t_[2]}));

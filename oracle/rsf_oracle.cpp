@@ -16,7 +16,7 @@
 // (not vendored under /root/reference) semantics that matter are restated from its published
 // headers: q*v = v + w*uv + q.vec x uv with uv = 2(q.vec x v) (Geometry/Quaternion.h
 // _transformVector); q.inverse() = conj(q)/|q|^2; hnormalized() = (x/z, y/z);
-// norm() = sqrt((x^2+y^2)+z^2); normalized() = v / norm (when norm^2 > 0).
+// norm() = sqrt(x^2+(y^2+z^2)) (Redux.h splits the range in halves: c0 + (c1 + c2)); normalized() = v / norm (when norm^2 > 0).
 //
 // Allocation semantics: the reference's bucket try-lock insert is lossy and non-deterministic
 // (utils/tsdf/voxel_hash.cu:71-76,93-105).  The oracle implements the *ideal* semantics
@@ -51,8 +51,8 @@ inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
 inline V3 neg(V3 a) { return {-a.x, -a.y, -a.z}; }
-inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-inline float norm(V3 a) { return std::sqrt((a.x * a.x + a.y * a.y) + a.z * a.z); }
+inline float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }   // Redux.h redux_novec_unroller: c0 + (c1 + c2)
+inline float norm(V3 a) { return std::sqrt(a.x * a.x + (a.y * a.y + a.z * a.z)); }
 inline V3 cross(V3 a, V3 b) {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
@@ -66,7 +66,7 @@ inline V3 qrot(Quat q, V3 v) {
 }
 // Eigen 3.3.7 QuaternionBase::inverse
 inline Quat qinv(Quat q) {
-  const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
+  const float n2 = (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);   // coeffs x,y,z,w reduced in halves
   if (n2 > 0.f) return {q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2};
   return {0.f, 0.f, 0.f, 0.f};
 }
@@ -415,7 +415,7 @@ void raycast(const Grid& g, float max_depth, int H, int W, const Intr& K, const 
     for (int x = 0; x < W; ++x) {
       const int idx = y * W + x;
       const V3 pc = Ki.mul(V3{(float)x, (float)y, 1.f});
-      const float n2 = (pc.x * pc.x + pc.y * pc.y) + pc.z * pc.z;
+      const float n2 = pc.x * pc.x + (pc.y * pc.y + pc.z * pc.z);
       const V3 dir_c = n2 > 0.f ? pc / std::sqrt(n2) : pc;
       const V3 dir_w = qrot(T_wc.q, dir_c);
       const V3 coarse = (dir_w * step_size) / g.vs;

@@ -57,8 +57,8 @@ __host__ __device__ inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b
 __host__ __device__ inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 __host__ __device__ inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
 __host__ __device__ inline V3 neg(V3 a) { return {-a.x, -a.y, -a.z}; }
-__host__ __device__ inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-__host__ __device__ inline float norm(V3 a) { return sqrtf((a.x * a.x + a.y * a.y) + a.z * a.z); }
+__host__ __device__ inline float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }   // Eigen redux order: c0 + (c1 + c2)
+__host__ __device__ inline float norm(V3 a) { return sqrtf(a.x * a.x + (a.y * a.y + a.z * a.z)); }
 __host__ __device__ inline V3 cross(V3 a, V3 b) {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
@@ -71,7 +71,7 @@ __host__ __device__ inline V3 qrot(Quat q, V3 v) {
   return {(v.x + q.w * uv.x) + c.x, (v.y + q.w * uv.y) + c.y, (v.z + q.w * uv.z) + c.z};
 }
 __host__ __device__ inline Quat qinv(Quat q) {
-  const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
+  const float n2 = (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);   // Eigen redux order for 4 coefficients
   if (n2 > 0.f) return {q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2};
   return {0.f, 0.f, 0.f, 0.f};
 }

@@ -1,0 +1,163 @@
+"""GPU parity tests against the REFERENCE ITSELF: RA-SLAM's unmodified utils/tsdf/*.cu, compiled for sm_100a
+against oracle/ref_shim (oracle/Makefile target _ref, oracle/ref_harness.cu) and run on the same B200 on the
+same seeded inputs as the product (called through the C ABI).
+
+What can and cannot be identical (measured, tests/tools/compare_reference.py):
+  * the reference build lets nvcc contract FMAs, the product computes every operation IEEE-rounded in source
+    order, so ~half of the TSDF words differ in the last bits; a voxel whose projection lands within ~1e-3 px
+    of a pixel-rounding tie (or whose sdf is within ~1e-5 of -truncation) can pick the neighbouring pixel /
+    the other branch -> a handful of voxels per million exceed the 1e-4 tolerance.  The tests bound their
+    number and check that (nearly) every one of them IS such a tie.
+  * the reference's insert takes a per-bucket try-lock and silently drops contended inserts
+    (utils/tsdf/voxel_hash.cu:71-75,93-104); the block is inserted a frame later.  The product inserts every
+    requested block at once, so per frame reference_set is a subset of product_set, equal at the end.
+    Voxels of blocks with a differing membership history are excluded from value comparisons.
+  * the reference never initialises rgb of an acquired block (utils/tsdf/voxel_mem.cu:44-51): recycled pool
+    slots start from the previous tenant's colours.  Colour is compared strictly only on blocks that never
+    held a recycled slot (alive since before the first carve, never removed).
+"""
+import numpy as np
+import pytest
+
+import parity
+import ref_lib
+
+pytestmark = pytest.mark.gpu
+
+TSDF_TOL = 1e-4        # BASELINE.json north_star: |dTSDF| <= 1e-4 (TSDF is stored in units of the truncation)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref/libref_tsdf.so not built (needs /root/reference: make -C oracle _ref)")
+    return ref_lib
+
+
+def _history(rsf, ref, seq, n, raycast_at=()):
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    r = ref.RefGrid(seq.voxel_size, seq.truncation)
+    cam = rsf.CameraParams(seq.K, seq.H, seq.W)
+    dirty, prev, first_removed, born_clean, ever_removed = set(), set(), None, set(), set()
+    rays = []
+    for i in range(n):
+        fr = seq.frame(i)
+        g.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        r.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        kg = set(parity.keys_of(g.ExportBlocks()[0]).tolist())
+        kr = set(parity.keys_of(r.ExportCoords()).tolist())
+        assert kr <= kg, f"frame {i}: reference allocated blocks the product did not: {len(kr - kg)}"
+        assert r.NumActiveBlock() == len(kr)
+        assert g.NumActiveBlock() == len(kg)
+        dirty |= kg ^ kr
+        ever_removed |= prev - kg
+        if first_removed is None and i and (prev - kg):
+            first_removed = i
+        if first_removed is None:
+            born_clean |= kg
+        prev = kg
+        if i in raycast_at:
+            rays.append((g.RayCast(seq.max_depth * 2, cam, seq.poses[i]), r.RayCast(seq.max_depth * 2, cam, seq.poses[i])))
+    return g, r, dirty, born_clean - ever_removed, rays
+
+
+def _tie_explained(seq, n, coords, vox):
+    """True where the voxel (block coords, linear index) projects within 2e-3 px of a rounding tie, or has an sdf
+    within 2e-5 of -truncation, in at least one of the first n frames."""
+    off = np.stack([vox & 7, (vox >> 3) & 7, vox >> 6], axis=1)
+    pw = (coords.astype(np.int64) * 8 + off).astype(np.float64) * seq.voxel_size
+    hit = np.zeros(len(vox), bool)
+    K = seq.K
+    for i in range(n):
+        T = seq.poses[i]
+        pc = pw @ T.rotation_matrix().T.astype(np.float64) + T.t.astype(np.float64)
+        z = pc[:, 2]
+        ok = z > 1e-6
+        zs = np.where(ok, z, 1.0)
+        u, v = K.fx * pc[:, 0] / zs + K.cx, K.fy * pc[:, 1] / zs + K.cy
+        inb = ok & (u > -0.5) & (u < seq.W - 0.5) & (v > -0.5) & (v < seq.H - 0.5)
+        fu, fv = np.abs(u - np.floor(u) - 0.5), np.abs(v - np.floor(v) - 0.5)
+        hit |= inb & ((fu < 2e-3) | (fv < 2e-3))
+        depth = seq.frame(i)[1]
+        ui = np.clip(np.rint(u), 0, seq.W - 1).astype(int)
+        vi = np.clip(np.rint(v), 0, seq.H - 1).astype(int)
+        d = depth[vi, ui]
+        xn, yn = (ui - K.cx) / K.fx, (vi - K.cy) / K.fy
+        sdf = np.sqrt(xn * xn + yn * yn + 1.0) * (d - z)
+        hit |= inb & (d > 0) & (np.abs(sdf + seq.truncation) < 2e-5)
+    return hit
+
+
+def _check_volume(rsf, ref, seq, n, raycast_at):
+    g, r, dirty, born_clean, rays = _history(rsf, ref, seq, n, raycast_at)
+    eg, er = g.ExportBlocks(), r.ExportBlocks()
+    kg, kr = parity.keys_of(eg[0]), parity.keys_of(er[0])
+    assert np.array_equal(kg, kr), "final allocated block-coordinate sets differ"          # identical sets
+    keep = ~np.isin(kg, np.array(sorted(dirty), dtype=np.uint64))
+    assert keep.mean() > 0.97
+    ta, tb = eg[1][keep], er[1][keep]
+    wa, wb = eg[2][keep][..., 3].astype(int), er[2][keep][..., 3].astype(int)
+    ca, cb = eg[2][keep][..., :3].astype(int), er[2][keep][..., :3].astype(int)
+    pa, pb = eg[3][keep], er[3][keep]
+    nvox = ta.size
+    # semantic labels identical (ties excepted)
+    lab = ((pa > 0.5) != (pb > 0.5)) & (np.abs(pa - 0.5) > 1e-6) & (np.abs(pb - 0.5) > 1e-6)
+    assert lab.sum() == 0, f"{lab.sum()} label mismatches"
+    # TSDF / weight within tolerance, apart from rounding-tie voxels
+    bad = (np.abs(ta - tb) > TSDF_TOL) | (wa != wb)
+    assert bad.sum() <= 1e-3 * nvox, f"{bad.sum()} of {nvox} voxels outside tolerance"
+    bi, vi = np.nonzero(bad)
+    if len(bi):
+        expl = _tie_explained(seq, n, eg[0][keep][bi], vi)
+        assert (~expl).sum() <= max(2, 0.01 * len(bi)), f"{(~expl).sum()} of {len(bi)} outliers are not rounding ties"
+    good = ~bad
+    assert np.abs(ta - tb)[good].max() <= TSDF_TOL
+    assert np.nanmax(np.abs(pa - pb)[good]) <= 1e-4, "fused probability differs beyond 1e-4 where TSDF/weight agree"
+    # colour: strict (+-1) on blocks alive since before the first carve and never re-allocated (no recycled pool slot)
+    strict = np.isin(kg[keep], np.array(sorted(born_clean), dtype=np.uint64))[:, None] & good & ((wa > 1) | (ta != -1))
+    off = (np.abs(ca - cb).max(axis=-1) > 1) & strict
+    assert off.sum() <= 1e-3 * max(strict.sum(), 1), f"{off.sum()} of {strict.sum()} voxels differ in colour by > 1"
+    # raycast: same hit mask up to a few tie pixels; colours equal on nearly all hit pixels
+    for a, b in rays:
+        ha, hb = a["rgba"][..., 3] > 0, b["rgba"][..., 3] > 0
+        assert hb.sum() > 0.2 * ha.size
+        assert (ha != hb).sum() <= 2e-3 * ha.size, f"hit masks differ in {(ha != hb).sum()} pixels"
+        both = ha & hb
+        d = np.abs(a["rgba"].astype(int) - b["rgba"].astype(int))[both].max(axis=-1)
+        dn = np.abs(a["normal"].astype(int) - b["normal"].astype(int))[both].max(axis=-1)
+        assert (d > 2).mean() <= 0.02, f"rgba differs on {(d > 2).mean():.4f} of hit pixels"
+        assert (dn > 2).mean() <= 0.02, f"normal image differs on {(dn > 2).mean():.4f} of hit pixels"
+    return g, r
+
+
+def test_reference_config1_room(rsf, ref, synth):
+    seq = synth.config1(n_frames=100, H=120, W=160, truncation=0.04)
+    _check_volume(rsf, ref, seq, 30, raycast_at=(19, 29))
+
+
+def test_reference_config2_tum_full_resolution(rsf, ref, synth):
+    seq = synth.config2(n_frames=60, H=480, W=640)
+    g, r = _check_volume(rsf, ref, seq, 40, raycast_at=(19, 39))
+    # GatherValidSemantic (utils/tsdf/voxel_tsdf.cu:504-530): same voxel positions bit for bit, values in tolerance
+    a, b = g.GatherValidSemantic(), r.GatherValidSemantic()
+    assert a.shape == b.shape and a.shape[1] == 5
+    oa, ob = np.lexsort(a[:, :3].T[::-1]), np.lexsort(b[:, :3].T[::-1])
+    a, b = a[oa], b[ob]
+    assert np.array_equal(a[:, :3].view(np.uint32), b[:, :3].view(np.uint32))
+    # all blocks here, including the ~1 % the reference inserted a frame late (one observation fewer)
+    assert (np.abs(a[:, 3] - b[:, 3]) > TSDF_TOL).mean() < 1e-2
+    # GatherValid and GatherVoxels (:476-502, :532-559)
+    va, vb = g.GatherValid(), r.GatherValid()
+    assert va.shape == vb.shape and va.shape[1] == 4
+    lo = np.asarray(seq.scene.room_min, np.float32) + 0.5
+    cube = rsf.BoundingCube(lo[0], lo[0] + 2.0, lo[1], lo[1] + 2.0, float(seq.scene.room_min[2]) - 0.2, lo[2] + 1.0)
+    qa, qb = g.GatherVoxels(cube), r.GatherVoxels(cube)
+    assert qa.shape == qb.shape and len(qa) > 0
+    qa, qb = qa[np.lexsort(qa[:, :3].T[::-1])], qb[np.lexsort(qb[:, :3].T[::-1])]
+    assert np.array_equal(qa[:, :3].view(np.uint32), qb[:, :3].view(np.uint32))
+
+
+def test_reference_truncation_6_voxels_long(rsf, ref, synth):
+    # trunc = 6 voxels: 3 samples per depth ray (utils/tsdf/voxel_tsdf.cu:154-166), more carving and re-allocation
+    seq = synth.config1(n_frames=100, H=120, W=160, truncation=0.06)
+    _check_volume(rsf, ref, seq, 60, raycast_at=(59,))
