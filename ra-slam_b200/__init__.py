@@ -23,7 +23,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsfusion.so")
+LIB_PATH = os.environ.get("RSF_LIBRARY") or os.path.join(_HERE, "librsfusion.so")   # RSF_LIBRARY: dev builds
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 
 RSF_OK, RSF_ERR_INVALID, RSF_ERR_CUDA, RSF_ERR_POOL_FULL, RSF_ERR_TABLE_FULL, RSF_ERR_CAPACITY = range(6)
