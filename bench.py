@@ -42,6 +42,9 @@ sys.path.insert(0, ROOT)
 os.environ["NCCL_DEBUG"] = os.environ.get("RSF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
 
 METRIC = "frames/s integrate+raycast 640x480 semantic (TUM fr1-shaped)"
+METRICS = {"tum": METRIC, "scannet": "frames/s integrate+raycast 640x480 semantic (ScanNet-shaped)",
+           "scannet-hires": "frames/s integrate+raycast 1296x968 semantic (ScanNet-shaped)",
+           "l515": "frames/s integrate+raycast 640x480 semantic (L515-shaped)"}
 UNIT = "frames/s"
 
 
@@ -53,6 +56,9 @@ def parse_args():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--workload", choices=["tum", "scannet", "scannet-hires", "l515"], default="tum",
+                    help="tum = BASELINE.json configs[1] (the headline line); the others are configs[2] / configs[3] shapes")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short 1296x968 ScanNet-shaped measurement")
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -62,8 +68,23 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+WORKLOADS = {
+    "tum": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame",
+    "scannet": "configs[2] ScanNet scene0-shaped 640x480 integrate+raycast per frame",
+    "scannet-hires": "configs[2] ScanNet scene0-shaped 1296x968 integrate+raycast per frame",
+    "l515": "configs[3] L515-shaped 640x480 integrate+raycast per frame",
+}
+
+
 def make_sequence(args, rank, n_frames):
     synth = importlib.import_module("ra-slam_b200.synth")
+    wl = getattr(args, "workload", "tum")
+    if wl == "scannet":
+        return synth.config3(n_frames=max(n_frames, 200))
+    if wl == "scannet-hires":
+        return synth.config3(n_frames=max(n_frames, 200), hires=True)
+    if wl == "l515":
+        return synth.config4(seed=10 + rank, n_frames=max(n_frames, 200))
     seq = synth.config2(n_frames=max(n_frames, 300), H=args.height, W=args.width)
     if rank:   # independent sequence per replica: same scene family, different seed
         sc = synth.room_scene(size=(5.0, 4.0, 2.8), n_boxes=4, seed=1 + 100 * rank)
@@ -226,7 +247,8 @@ def run_reference(args):
             use_ref = torch.cuda.is_available()
         except Exception:
             use_ref = False
-    cfg = {"workload": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame"}
+    cfg = {"workload": WORKLOADS[args.workload]}
+    secondary = None
     if use_ref:
         seq = make_sequence(args, 0, W + K)
         frames = render_frames(seq, W + K)
@@ -242,6 +264,14 @@ def run_reference(args):
                "pageable_inputs_value": fps_pg, "pinned_inputs_value": fps_pin, **br}
         e2e = {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 0}
         cfg["parallelism"] = "1 grid, reference CUDA build"
+        if args.workload == "tum" and not args.no_secondary:
+            synth = importlib.import_module("ra-slam_b200.synth")
+            s2 = synth.config3(n_frames=200, hires=True)
+            f2 = render_frames(s2, SEC_W + SEC_K)
+            v_pg, _ = reference_gpu_fps(s2, f2, SEC_W, SEC_K, pinned=False)
+            v_pin, b2 = reference_gpu_fps(s2, f2, SEC_W, SEC_K, pinned=True)
+            secondary = {"workload": WORKLOADS["scannet-hires"], "steps": SEC_K, "warmup": SEC_W, "unit": UNIT,
+                         "value": max(v_pg, v_pin), "pageable_inputs_value": v_pg, "pinned_inputs_value": v_pin, **b2}
     else:
         # bounded sample: each step is one frame; cap the run to a few minutes of CPU work
         K = min(K, 60)
@@ -257,11 +287,95 @@ def run_reference(args):
     cfg.update({"height": seq.H, "width": seq.W, "voxel_size": seq.voxel_size, "truncation": seq.truncation,
                 "max_depth": seq.max_depth, "raycast_max_depth": seq.max_depth * 2})
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "impl": "reference", "metric": METRICS[args.workload], "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 0,
     }
+    if secondary:
+        line["scannet_1296x968"] = secondary
     print(json.dumps(line), flush=True)
+
+
+SEC_K, SEC_W = 60, 12     # the short secondary measurement (BASELINE.json's metric also names 1296x968)
+
+
+def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
+    """Short form of the two arms of run_native for a secondary workload: device-resident frames/s (CUDA
+    events, L2 flushed between steps) and pipelined end-to-end frames/s with pinned host buffers."""
+    H, Wd = seq.H, seq.W
+    cam = rsf.CameraParams(seq.K, H, Wd)
+    rmax = seq.max_depth * 2
+    stream = torch.cuda.current_stream()
+    grid = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank, stream=stream.cuda_stream)
+    d_frames = [tuple(torch.from_numpy(a).to(dev) for a in fr) for fr in frames]
+    out = {"rgba": torch.empty((H, Wd, 4), dtype=torch.uint8, device=dev),
+           "normal": torch.empty((H, Wd, 4), dtype=torch.uint8, device=dev),
+           "depth": torch.empty((H, Wd), dtype=torch.float32, device=dev)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for i in range(W):
+        grid.Integrate(*d_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid.RayCast(rmax, cam, seq.poses[i], out=out)
+    grid.synchronize()
+    tot0 = grid.totals()
+    grid.profile_enable(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.zero_()
+        ev[k][0].record()
+        grid.Integrate(*d_frames[W + k], seq.max_depth, seq.K, seq.poses[W + k])
+        grid.RayCast(rmax, cam, seq.poses[W + k], out=out)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    prof = grid.profile_read()
+    tot1 = grid.totals()
+    grid.close()
+    del d_frames
+    grid_e = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank)
+    pins, h_frames = [], []
+    for fr in frames:
+        row = []
+        for a in fr:
+            pa = rsf.PinnedArray(a.shape, a.dtype)
+            pa.array[...] = a
+            pins.append(pa)
+            row.append(pa.array)
+        h_frames.append(tuple(row))
+    h_outs = []
+    for _ in range(2):
+        d = {}
+        for kname, shape, dt in (("rgba", (H, Wd, 4), np.uint8), ("normal", (H, Wd, 4), np.uint8), ("depth", (H, Wd), np.float32)):
+            pa = rsf.PinnedArray(shape, dt)
+            pins.append(pa)
+            d[kname] = pa.array
+        h_outs.append(d)
+    for i in range(W):
+        grid_e.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        grid_e.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prev = None
+    for k in range(K):
+        i = W + k
+        grid_e.IntegrateAsync(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
+        t = grid_e.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k & 1])
+        if prev is not None:
+            grid_e.wait(prev)
+        prev = t
+    grid_e.wait(prev)
+    grid_e.synchronize()
+    e2e_s = time.perf_counter() - t0
+    grid_e.close()
+    P = H * Wd
+    upd = tot1["updated_voxels"] - tot0["updated_voxels"]
+    vis = tot1["visible_blocks"] - tot0["visible_blocks"]
+    int_ms, int_n = prof["integrate"]
+    alg = 24.0 * upd + 12.0 * vis + 15.0 * P * int_n
+    return {"steps": K, "warmup": W, "unit": UNIT, "value": K / (dev_ms * 1e-3), "ms_per_step": dev_ms / K,
+            "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 12 * P},
+            "kernels_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
+            "integrate_achieved_gbs": alg / (int_ms * 1e-3) / 1e9 if int_ms else None,
+            "updated_voxels_per_launch": upd / max(int_n, 1), "visible_blocks_per_launch": vis / max(int_n, 1)}
 
 
 def run_native(args):
@@ -428,10 +542,10 @@ def run_native(args):
     kernels = {k: {"ms_per_launch": (v[0] / v[1] if v[1] else None), "launches": v[1],
                    "share_of_step": (v[0] / dev_ms if dev_ms else None)} for k, v in prof.items()}
     line = {
-        "metric": METRIC, "value": world * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "metric": METRICS[args.workload], "value": world * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] TUM fr1-shaped 640x480 integrate+raycast per frame", "height": H, "width": Wd,
+        "config": {"workload": WORKLOADS[args.workload], "height": H, "width": Wd,
                    "voxel_size": seq.voxel_size, "truncation": seq.truncation, "max_depth": seq.max_depth,
                    "raycast_max_depth": rmax, "semantic_classes": 2,
                    "l2": "flushed: 256 MiB memset between steps, outside the timed events",
@@ -454,6 +568,14 @@ def run_native(args):
         "clocks": clocks,
         "map": {"active_blocks": stats_end["active_blocks"], "high_water": stats_end["high_water"]},
     }
+    if world == 1 and args.workload == "tum" and not args.no_secondary:
+        synth = importlib.import_module("ra-slam_b200.synth")
+        s2 = synth.config3(n_frames=200, hires=True)
+        sec = quick_native(rsf, torch, dev, local_rank, s2, render_frames(s2, SEC_W + SEC_K), SEC_W, SEC_K)
+        sec["workload"] = WORKLOADS["scannet-hires"]
+        peak_s, _ = measured_peak_gbs()
+        sec["integrate_roofline_frac"] = (sec["integrate_achieved_gbs"] or 0.0) / peak_s
+        line["scannet_1296x968"] = sec
     if not args.no_cpu_baseline:
         s = min(args.cpu_sample_frames, K)
         cores = os.cpu_count() or 1

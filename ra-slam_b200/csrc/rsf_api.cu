@@ -103,6 +103,9 @@ int make_frame(rsf_grid_t g, int H, int W, float max_depth, const float* K, cons
   if (!K || !pose) return fail(RSF_ERR_INVALID, "K / pose must not be NULL");
   if (H <= 0 || W <= 0 || (size_t)H * (size_t)W > g->max_pixels)
     return fail(RSF_ERR_INVALID, "image %dx%d outside (0, max_pixels=%zu]", W, H, g->max_pixels);
+  // the kernels divide by truncation / max_depth through a shared refined reciprocal: keep both well inside
+  // the normal range (any physical value is)
+  if (!(max_depth >= 1e-6f && max_depth <= 1e6f)) return fail(RSF_ERR_INVALID, "max_depth %g outside [1e-6, 1e6] m", (double)max_depth);
   f->K = Intr{K[0], K[1], K[2], K[3]};
   f->Ki = f->K.inverse();                       // CameraParams ctor, camera.cuh:61-67
   f->T_cw = Pose{Quat{pose[0], pose[1], pose[2], pose[3]}, V3{pose[4], pose[5], pose[6]}};
@@ -258,7 +261,8 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   if (o.shard_world <= 0) o.shard_world = 1;
   if (o.shard_shift < 0) o.shard_shift = d.shard_shift;
   if (o.shard_halo < 0) o.shard_halo = d.shard_halo;
-  if (!(o.voxel_size > 0.f) || !(o.truncation > 0.f)) return fail(RSF_ERR_INVALID, "voxel_size and truncation must be > 0");
+  if (!(o.voxel_size >= 1e-6f && o.voxel_size <= 1e6f) || !(o.truncation >= 1e-6f && o.truncation <= 1e6f))
+    return fail(RSF_ERR_INVALID, "voxel_size and truncation must lie in [1e-6, 1e6] m");
   if (o.table_slots_log2 > 30 || ((size_t)1 << o.table_slots_log2) < 2 * (size_t)o.pool_blocks)
     return fail(RSF_ERR_INVALID, "table_slots_log2=%d must give >= 2x pool_blocks=%d slots", o.table_slots_log2, o.pool_blocks);
   if (o.shard_rank < 0 || o.shard_rank >= o.shard_world) return fail(RSF_ERR_INVALID, "shard_rank outside [0, shard_world)");

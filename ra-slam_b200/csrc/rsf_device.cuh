@@ -151,7 +151,7 @@ struct __align__(16) VisEntry {
 };
 
 // One pixel of the staged frame: 16 B, gathered with one 128-bit load per voxel.
-//   x = depth [m], y = rgb (r | g<<8 | b<<16 bits), z = ln ht - ln lt, w = w_new = (1 - depth/max_depth)*4
+//   x = depth [m], y = rgb (r | g<<8 | b<<16 bits), z = ln ht - ln lt, w = depth_to_range = |K^-1 (u,v,1)|
 typedef float4 FramePixel;
 
 // View of one grid's device memory; passed to kernels by value.
