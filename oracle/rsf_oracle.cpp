@@ -28,6 +28,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include "../ra-slam_b200/csrc/rsf_mc_table.h"   // packed classic marching-cubes triangle table (data only)
 #include <memory>
 #include <thread>
 #include <unordered_map>
@@ -628,6 +629,106 @@ int64_t ora_gather_voxels(ora_grid* o, const float* bounds6, float* rows) {
     if (x >= b[0] && y >= b[2] && z >= b[4] && x + 7 <= b[1] && y + 7 <= b[3] && z + 7 <= b[5]) sel.push_back(B);
   }
   return gather_rows(o->g, sel, 4, rows);
+}
+
+// ---- TSDFGrid::GatherValidMesh, voxel_tsdf.cu:561-845 (marching_cube_kernel + the two compactions) -------------
+// Tables: corner offsets / edges / edge->lattice vertex in the reference's numbering (mcube_table.cuh:14-31); the
+// 256-case triangle table is the classic public one, shared with the product as packed data (rsf_mc_table.h).
+static const int kMcCorner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 0, 1}, {0, 0, 1}, {0, 1, 0}, {1, 1, 0}, {1, 1, 1}, {0, 1, 1}};
+static const int kMcDimCorner[3] = {1, 4, 3};                                   // offset_dim_indics
+static const int kMcEdge[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+static const int kMcEdgeVertex[12][2] = {{0, 0}, {1, 2}, {3, 0}, {0, 2}, {4, 0}, {5, 2}, {7, 0}, {4, 2}, {0, 1}, {1, 1}, {2, 1}, {3, 1}};
+static const uint64_t kMcTri[256] = {RSF_MC_TRI_TABLE};
+static inline int mc_tri(int cubeindex, int k) {      // tri_table[cubeindex][k], -1 past the end
+  if (k >= 15) return -1;
+  const int e = (int)((kMcTri[cubeindex] >> (4 * k)) & 15u);
+  return e == 15 ? -1 : e;
+}
+
+// Outputs (any may be NULL to size): vertices nv x 3, vertex_prob nv, triangles nt x 3.  Order: blocks in sorted
+// key order; inside a block, vertices by lattice index (cube_idx * 3 + dim), triangles by voxel then slot --
+// what the reference's stable compaction produces for its own block order.
+int64_t ora_gather_valid_mesh(ora_grid* o, float* vertices, float* vertex_prob, int32_t* triangles, int64_t* n_triangles) {
+  const Grid& g = o->g;
+  int64_t nv = 0, nt = 0;
+  static thread_local std::vector<float> cube_t, cube_p;
+  cube_t.assign(16 * 16 * 16, 0.f);
+  cube_p.assign(16 * 16 * 16, 0.f);
+  auto C = [](int z, int y, int x) { return (z * 16 + y) * 16 + x; };
+  for (const Block* B : sorted_blocks(g)) {
+    // :589-635 the 2x2x2 block neighbourhood; weight <= 10 or missing block -> tsdf -10, prob 0
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k) {
+          const Block* N = g.find(S3{(int16_t)(B->pos.x + k), (int16_t)(B->pos.y + j), (int16_t)(B->pos.z + i)});
+          for (int v = 0; v < kBlockVol; ++v) {
+            const int x = v & 7, y = (v >> 3) & 7, z = v >> 6;
+            float t = -10.f, p = 0.f;
+            if (N && (int)N->rgbw[4 * v + 3] > 10) {
+              t = N->tsdf[v];
+              p = N->prob[v];
+            }
+            cube_t[C(i * 8 + z, j * 8 + y, k * 8 + x)] = t;
+            cube_p[C(i * 8 + z, j * 8 + y, k * 8 + x)] = p;
+          }
+        }
+    // :672-712 triangles, marking referenced lattice vertices
+    std::vector<uint8_t> vmask(9 * 9 * 9 * 3, 0);
+    std::vector<int> tri;   // lattice ids, 3 per valid triangle
+    for (int v = 0; v < kBlockVol; ++v) {
+      const int x = v & 7, y = (v >> 3) & 7, z = v >> 6;
+      float lt[8];
+      int cubeindex = 0;
+      for (int i = 0; i < 8; ++i) {
+        lt[i] = cube_t[C(z + kMcCorner[i][2], y + kMcCorner[i][1], x + kMcCorner[i][0])];
+        cubeindex |= ((lt[i] < 0) << i);
+      }
+      for (int i = 0; i < 5; ++i) {
+        if (mc_tri(cubeindex, i * 3) == -1) continue;
+        bool valid = true;
+        int ids[3];
+        for (int j = 0; j < 3; ++j) {
+          const int e = mc_tri(cubeindex, i * 3 + j);
+          const int v1 = kMcEdge[e][0], v2 = kMcEdge[e][1];
+          if (std::fabs(lt[v2] - lt[v1]) < 1e-3 || std::fabs(lt[v2] - lt[v1]) >= 2) {
+            valid = false;
+            break;
+          }
+          const int lc = kMcEdgeVertex[e][0], dim = kMcEdgeVertex[e][1];
+          const int cell = (kMcCorner[lc][2] + z) * 81 + (kMcCorner[lc][1] + y) * 9 + (kMcCorner[lc][0] + x);
+          ids[j] = cell * 3 + dim;
+          vmask[ids[j]] = 1;
+        }
+        if (valid) tri.insert(tri.end(), ids, ids + 3);
+      }
+    }
+    // :639-668 vertices + compaction (stable, by lattice index)
+    std::vector<int> rank(vmask.size(), -1);
+    for (size_t l = 0; l < vmask.size(); ++l) {
+      if (!vmask[l]) continue;
+      rank[l] = (int)nv;
+      if (vertices) {
+        const int cell = (int)l / 3, j = (int)l % 3;
+        const int vx = cell % 9, vy = cell / 9 % 9, vz = cell / 81;
+        const int* off = kMcCorner[kMcDimCorner[j]];
+        const float t1 = cube_t[C(vz, vy, vx)], t2 = cube_t[C(vz + off[2], vy + off[1], vx + off[0])];
+        const float p1 = cube_p[C(vz, vy, vx)], p2 = cube_p[C(vz + off[2], vy + off[1], vx + off[0])];
+        const float s = (-t1) / (t2 - t1);
+        const float v1[3] = {(float)(int16_t)((int16_t)(B->pos.x << 3) + vx), (float)(int16_t)((int16_t)(B->pos.y << 3) + vy),
+                             (float)(int16_t)((int16_t)(B->pos.z << 3) + vz)};
+        for (int c = 0; c < 3; ++c) vertices[3 * nv + c] = (v1[c] + s * (float)off[c]) * g.vs;
+        if (vertex_prob) vertex_prob[nv] = (p1 + p2) / 2;
+      }
+      ++nv;
+    }
+    for (size_t k = 0; k < tri.size(); k += 3) {
+      if (triangles)
+        for (int j = 0; j < 3; ++j) triangles[3 * nt + j] = rank[tri[k + j]];
+      ++nt;
+    }
+  }
+  if (n_triangles) *n_triangles = nt;
+  return nv;
 }
 
 }  // extern "C"

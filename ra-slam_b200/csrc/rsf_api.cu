@@ -516,9 +516,48 @@ int rsf_gather_voxels(rsf_grid_t g, const float bounds[6], float* rows, int64_t 
   return gather_rows(g, 1, bounds, 4, rows, cap_rows, n_rows);
 }
 
-int rsf_gather_valid_mesh(rsf_grid_t g, float*, int64_t, int64_t*, int32_t*, int64_t, int64_t*, float*) {
+int rsf_gather_valid_mesh(rsf_grid_t g, float* vertices, int64_t cap_vertices, int64_t* n_vertices, int32_t* triangles,
+                          int64_t cap_triangles, int64_t* n_triangles, float* vertex_prob) {
   if (int rc = check_grid(g)) return rc;
-  return fail(RSF_ERR_INVALID, "rsf_gather_valid_mesh: marching cubes not implemented yet");
+  if (!n_vertices || !n_triangles) return fail(RSF_ERR_INVALID, "n_vertices / n_triangles must not be NULL");
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
+  launch_gather_select(g->view, 0, g->opt.shard_world > 1, S3{0, 0, 0}, S3{0, 0, 0}, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (int rc = sync_counters(g)) return rc;
+  const int nblk = g->h_ctr->gather_count;
+  DevBuf<int2> counts(g->stream), offsets(g->stream);
+  DevBuf<long long> totals(g->stream);
+  RSF_CUDA(counts.alloc(nblk));
+  RSF_CUDA(offsets.alloc(nblk));
+  RSF_CUDA(totals.alloc(2));
+  launch_mesh_count(g->view, nblk, counts.p, offsets.p, totals.p, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  long long h_tot[2] = {0, 0};
+  RSF_CUDA(cudaMemcpyAsync(h_tot, totals.p, sizeof(h_tot), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  *n_vertices = h_tot[0];
+  *n_triangles = h_tot[1];
+  if (h_tot[0] > 0x7fffffffLL || h_tot[1] > 0x7fffffffLL) return fail(RSF_ERR_CAPACITY, "mesh exceeds 2^31 elements");
+  if (!vertices && !triangles && !vertex_prob) return RSF_OK;        // size query
+  if (!vertices || !triangles || !vertex_prob)
+    return fail(RSF_ERR_INVALID, "vertices, triangles and vertex_prob must be given together");
+  if (cap_vertices < h_tot[0] || cap_triangles < h_tot[1])
+    return fail(RSF_ERR_CAPACITY, "need %lld vertices / %lld triangles, capacity %lld / %lld", h_tot[0], h_tot[1],
+                (long long)cap_vertices, (long long)cap_triangles);
+  if (h_tot[0] == 0 && h_tot[1] == 0) return RSF_OK;
+  DevBuf<float> dv(g->stream), dp(g->stream);
+  DevBuf<int> dt(g->stream);
+  RSF_CUDA(dv.alloc((size_t)h_tot[0] * 3));
+  RSF_CUDA(dp.alloc((size_t)h_tot[0]));
+  RSF_CUDA(dt.alloc((size_t)h_tot[1] * 3));
+  launch_mesh_emit(g->view, g->opt.voxel_size, nblk, offsets.p, dv.p, dp.p, dt.p, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  RSF_CUDA(cudaMemcpyAsync(vertices, dv.p, (size_t)h_tot[0] * 3 * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(vertex_prob, dp.p, (size_t)h_tot[0] * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(triangles, dt.p, (size_t)h_tot[1] * 3 * sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
 }
 
 int rsf_export_blocks(rsf_grid_t g, int owned_only, int16_t* coords, float* tsdf, uint8_t* rgbw, float* prob,

@@ -25,6 +25,10 @@ void launch_retrieve_voxels(const GridView& g, const short* pts, int n, float* t
                             uint8_t* found, cudaStream_t s);
 void launch_assign_voxels(const GridView& g, const short* pts, int n, const float* tsdf, const uint32_t* rgbw,
                           const float* prob, uint8_t* written, cudaStream_t s);
+// rsf_mesh.cu: marching cubes over gather_list[0 .. nblk): count + scan, then emit into exact-size arrays
+void launch_mesh_count(const GridView& g, int nblk, int2* counts, int2* offsets, long long* totals, cudaStream_t s);
+void launch_mesh_emit(const GridView& g, float vs, int nblk, const int2* offsets, float* vertices, float* vprob,
+                      int* triangles, cudaStream_t s);
 void launch_trilinear(const GridView& g, const float* pts, int n, float* out, cudaStream_t s);
 
 }  // namespace rsf

@@ -55,6 +55,8 @@ def load():
     for n in ("ora_gather_valid", "ora_gather_valid_semantic"):
         getattr(lib, n).restype = C.c_int64
         getattr(lib, n).argtypes = [_P, _P]
+    lib.ora_gather_valid_mesh.restype = C.c_int64
+    lib.ora_gather_valid_mesh.argtypes = [_P, _P, _P, _P, _P]
     lib.ora_gather_voxels.restype = C.c_int64
     lib.ora_gather_voxels.argtypes = [_P, _P, _P]
     _lib = lib
@@ -130,6 +132,16 @@ class OracleGrid:
     def GatherVoxels(self, volumn):
         b = volumn.as_array()
         return self._rows(self.lib.ora_gather_voxels, 4, b.ctypes.data)
+
+    def GatherValidMesh(self):
+        nt = C.c_int64(0)
+        nv = int(self.lib.ora_gather_valid_mesh(self.h, None, None, None, C.byref(nt)))
+        v = np.empty((nv, 3), np.float32)
+        p = np.empty(nv, np.float32)
+        t = np.empty((nt.value, 3), np.int32)
+        if nv or nt.value:
+            self.lib.ora_gather_valid_mesh(self.h, v.ctypes.data, p.ctypes.data, t.ctypes.data, C.byref(nt))
+        return v, t, p
 
     # table-level
     def AllocateBlocks(self, coords):

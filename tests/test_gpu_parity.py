@@ -319,3 +319,35 @@ def test_cpp_adapter_tsdf_system(rsf, synth, tmp_path):
     assert np.array_equal(se3[0], A.as_array()) and np.array_equal(se3[1], B.as_array())
     assert np.allclose(rsf.SE3(se3[2][:4], se3[2][4:]).matrix(), A.matrix() @ B.matrix(), atol=1e-5)
     assert np.allclose(rsf.SE3(se3[3][:4], se3[3][4:]).matrix(), np.linalg.inv(A.matrix()), atol=1e-5)
+
+
+# ---- GatherValidMesh (marching cubes, voxel_tsdf.cu:561-845) ---------------------------------------
+def _soup(v, t, p):
+    """Order-independent form of an indexed mesh: one row per triangle (9 coordinates + 3 probabilities), sorted."""
+    rows = np.concatenate([v[t].reshape(len(t), 9), p[t].reshape(len(t), 3)], axis=1)
+    return rows[np.lexsort(rows[:, :9].T[::-1])]
+
+
+def test_mesh_matches_oracle(rsf, synth):
+    seq = synth.config2(n_frames=300, H=120, W=160)
+    g, o, _ = _run_both(rsf, seq, 24)
+    v, t, p = g.GatherValidMesh()
+    vo, to, po = o.GatherValidMesh()
+    assert len(t) > 50_000 and v.shape == vo.shape and t.shape == to.shape, (v.shape, vo.shape, t.shape, to.shape)
+    assert t.min() >= 0 and t.max() < len(v)
+    assert len(np.unique(t)) >= 0.99 * len(v)      # the rest: vertices marked by a triangle that a later edge dropped
+    a, b = _soup(v, t, p), _soup(vo, to, po)
+    assert np.array_equal(a[:, :9].view(np.uint32), b[:, :9].view(np.uint32))          # positions bit-exact
+    assert np.abs(a[:, 9:] - b[:, 9:]).max() <= 1e-5                                    # probabilities (logit storage)
+    # vertex multiset as well (vertices referenced only by dropped triangles are still emitted, as in the reference)
+    sv, so = v[np.lexsort(v.T[::-1])], vo[np.lexsort(vo.T[::-1])]
+    assert np.array_equal(sv.view(np.uint32), so.view(np.uint32))
+
+
+def test_mesh_empty_and_capacity(rsf):
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=1024, table_slots_log2=12)
+    v, t, p = g.GatherValidMesh()
+    assert v.shape == (0, 3) and t.shape == (0, 3) and p.shape == (0,)
+    g.AllocateBlocks([[0, 0, 0], [1, 0, 0]])           # fresh blocks: weight 1 -> everything reads -10, no surface
+    v, t, p = g.GatherValidMesh()
+    assert len(v) == 0 and len(t) == 0

@@ -161,3 +161,31 @@ def test_reference_truncation_6_voxels_long(rsf, ref, synth):
     # trunc = 6 voxels: 3 samples per depth ray (utils/tsdf/voxel_tsdf.cu:154-166), more carving and re-allocation
     seq = synth.config1(n_frames=100, H=120, W=160, truncation=0.06)
     _check_volume(rsf, ref, seq, 60, raycast_at=(59,))
+
+
+def test_reference_mesh(rsf, ref, synth):
+    """GatherValidMesh (utils/tsdf/voxel_tsdf.cu:736-845) against the reference's own marching cubes."""
+    from scipy.spatial import cKDTree
+    seq = synth.config2(n_frames=60, H=240, W=320)
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    r = ref.RefGrid(seq.voxel_size, seq.truncation)
+    for i in range(40):
+        fr = seq.frame(i)
+        g.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        r.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+    v, t, p = g.GatherValidMesh()
+    vr, tr, pr = r.GatherValidMesh()
+    assert len(tr) > 50_000
+    # same surface: counts within 1 % (weight-10 threshold ties, late blocks), every vertex has a partner within
+    # 0.05 voxel in the other mesh for >= 99 % of vertices, with matching probability
+    assert abs(len(t) - len(tr)) <= 0.01 * len(tr), (len(t), len(tr))
+    assert abs(len(v) - len(vr)) <= 0.01 * len(vr), (len(v), len(vr))
+    for a, pa, b, pb in ((v, p, vr, pr), (vr, pr, v, p)):
+        d, j = cKDTree(b).query(a)
+        near = d <= 0.05 * seq.voxel_size
+        assert near.mean() >= 0.99, near.mean()
+        assert np.abs(pa[near] - pb[j[near]]).max() <= 0.05 and np.abs(pa[near] - pb[j[near]]).mean() <= 1e-3
+    # triangles: centroids match the same way
+    ca, cb = v[t].mean(axis=1), vr[tr].mean(axis=1)
+    d, _ = cKDTree(cb).query(ca)
+    assert (d <= 0.05 * seq.voxel_size).mean() >= 0.99

@@ -165,3 +165,34 @@ def test_gather_formats_and_bounds(synth, rsf):
     half = g.GatherVoxels(rsf.BoundingCube(lo[0], mid[0], lo[1], hi[1], lo[2], hi[2]))
     assert 0 < len(half) < len(rows4) and len(half) % 512 == 0
     assert half[:, 0].max() <= mid[0] + 1e-6
+
+
+def test_marching_cubes_on_a_sphere():
+    # known-answer test of the oracle's GatherValidMesh (voxel_tsdf.cu:561-845) on an analytic signed distance
+    # field: a sphere of radius 9.3 voxels, weight 20 everywhere (> 10, so every voxel takes part)
+    vs, r, c = 0.02, 9.3, np.array([16.2, 15.7, 16.4])
+    g = OracleGrid(vs, 0.06, 1)
+    blocks = np.array([[x, y, z] for x in range(4) for y in range(4) for z in range(4)], np.int16)
+    g.AllocateBlocks(blocks)
+    pts = np.array([[x, y, z] for x in range(32) for y in range(32) for z in range(32)], np.int16)
+    sdf = (np.linalg.norm(pts - c, axis=1) - r) / 3.0            # truncation = 3 voxels
+    tsdf = np.clip(sdf, -1, 1).astype(np.float32)
+    rgbw = np.tile(np.array([[10, 20, 30, 20]], np.uint8), (len(pts), 1))
+    assert g.Assign(pts, tsdf=tsdf, rgbw=rgbw, prob=np.full(len(pts), 0.25, np.float32)).all()
+    v, t, p = g.GatherValidMesh()
+    assert len(t) > 1000 and t.min() >= 0 and t.max() < len(v)
+    rad = np.linalg.norm(v / vs - c, axis=1)
+    assert np.abs(rad - r).max() < 0.05, np.abs(rad - r).max()          # linear interpolation error on a sphere
+    assert np.allclose(p, 0.25)
+    # the sphere lies strictly inside the 4x4x4 blocks: the surface is closed.  Vertices are per block lattice
+    # (duplicated across block faces), so weld by position before counting: V - E + F = 2
+    key = np.round(v / vs * 4096).astype(np.int64)
+    _, inv = np.unique(key, axis=0, return_inverse=True)
+    tw = inv.reshape(-1)[t]
+    tw = tw[(tw[:, 0] != tw[:, 1]) & (tw[:, 1] != tw[:, 2]) & (tw[:, 0] != tw[:, 2])]
+    edges = np.sort(np.concatenate([tw[:, [0, 1]], tw[:, [1, 2]], tw[:, [2, 0]]]), axis=1)
+    ue, cnt = np.unique(edges, axis=0, return_counts=True)
+    assert (cnt == 2).all()                                              # watertight 2-manifold
+    assert len(np.unique(tw)) - len(ue) + len(tw) == 2                   # Euler characteristic of a sphere
+    area = 0.5 * np.linalg.norm(np.cross(v[t[:, 1]] - v[t[:, 0]], v[t[:, 2]] - v[t[:, 0]]), axis=1).sum()
+    assert abs(area / (4 * np.pi * (r * vs) ** 2) - 1) < 0.02
