@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--pool-log2", type=int, default=21)
     ap.add_argument("--shift", type=int, default=4)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--merge", choices=["fused", "nccl"], default="fused",
+                    help="fused = raycast + min-depth merge in one kernel over NVLink peer memory; nccl = all_reduce(MIN)")
     ap.add_argument("--gpus", type=int, default=0)
     args = ap.parse_args()
     import torch
@@ -64,6 +66,7 @@ def main():
            "prob": torch.empty((H, Wd), dtype=torch.float32, device=dev)}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     merged = None
+    fused = shard.FusedMinDepthMerge(H, Wd, dev, n_planes=3) if (world > 1 and args.merge == "fused") else None
 
     phase_ev = []          # (name, start, stop) CUDA events of the timed steps
 
@@ -85,8 +88,11 @@ def main():
             phase("broadcast", lambda: dist.broadcast(buf, src=0), timed)
         fr = shard.unpack_frame(buf, H, Wd)
         phase("integrate", lambda: grid.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i]), timed)
-        phase("raycast", lambda: grid.RayCast(rmax, cam, seq.poses[i], out=out), timed)
-        merged = phase("merge", lambda: shard.merge_raycast_min_depth(out), timed) if world > 1 else out
+        if fused is not None:
+            merged = phase("raycast+merge", lambda: fused.raycast(grid, rmax, cam, seq.poses[i], out, rearm_barrier=False), timed)
+        else:
+            phase("raycast", lambda: grid.RayCast(rmax, cam, seq.poses[i], out=out), timed)
+            merged = phase("merge", lambda: shard.merge_raycast_min_depth(out), timed) if world > 1 else out
         if ref is not None:
             ref.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
 
@@ -151,7 +157,10 @@ def main():
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[4] multi-room building 16x12 m, voxel 0.005, trunc 0.03, max_depth 8, 640x480",
                            "shard_shift": args.shift, "halo_blocks": 1, "pool_blocks": 1 << args.pool_log2,
-                           "collectives_per_step": "1 ncclBroadcast (packed frame) + 1 ncclAllReduce(MIN, int64 x3 planes)",
+                           "collectives_per_step": ("1 ncclBroadcast (packed frame); raycast + min-depth merge fused: system-scope atomicMin "
+                                                    "into the presenting rank's planes over NVLink peer memory + 1 symmetric-memory barrier (the next frame's "
+                                                    "broadcast orders the re-arming of the planes)")
+                           if fused is not None else "1 ncclBroadcast (packed frame) + 1 ncclAllReduce(MIN, int64 x3 planes)",
                            "l2": "flushed: 256 MiB memset between steps, outside the timed events"},
                 "voxel_updates_per_s_all_ranks": float(sm[1]) / (ms_max * 1e-3),
                 "active_blocks_sum_over_ranks": float(sm[2]), "active_blocks_max_rank": float(mx[2]),

@@ -128,6 +128,19 @@ RSF_API int rsf_wait(rsf_grid_t g, int ticket);
 RSF_API int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
                        uint8_t* rgba, uint8_t* normal, float* depth, float* prob);
 
+/* Spatially sharded grids (rsf_options.shard_world > 1): raycast with the per-pixel min-depth merge fused into the
+ * kernel (new; the reference is single-GPU).  merge_planes points to n_planes * H * W 64-bit words preset to all-ones --
+ * normally the PRESENTING rank's buffer, mapped into this process as NVLink peer memory (torch symmetric memory,
+ * cudaIpc, ...).  Every hit this rank owns is one system-scope atomicMin per plane of (depth bits << 32 | payload):
+ * plane 0 payload = RGBA8, plane 1 = the normal image, plane 2 = probability bits.  Asynchronous on the grid's stream;
+ * no image is written locally. */
+RSF_API int rsf_raycast_merge_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
+                                     uint64_t* merge_planes, int n_planes);
+/* On the presenting rank, after all ranks' rsf_raycast_merge_device kernels have completed (cross-rank barrier):
+ * unpack the planes into the reference's images (+ depth / prob, any may be NULL) and reset the planes to all-ones. */
+RSF_API int rsf_merge_finalize_device(rsf_grid_t g, int H, int W, uint64_t* merge_planes, int n_planes, uint8_t* rgba,
+                                      uint8_t* normal, float* depth, float* prob);
+
 /* Block until everything enqueued on the grid's stream is done; surfaces device-side errors
  * (pool/table exhaustion) of the asynchronous variants. */
 RSF_API int rsf_synchronize(rsf_grid_t g);

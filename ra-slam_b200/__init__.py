@@ -65,6 +65,8 @@ ABI = {
     "rsf_integrate_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
     "rsf_raycast": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
+    "rsf_raycast_merge_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, C.c_int]),
+    "rsf_merge_finalize_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
     "rsf_synchronize": (C.c_int, [_P]),
     "rsf_num_active_blocks": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rsf_get_stats": (C.c_int, [_P, C.POINTER(rsf_frame_stats)]),
@@ -312,6 +314,20 @@ class TSDFGrid:
         _check(self._lib.rsf_raycast(self._h, max_depth, H, W, _fptr(K), _fptr(pose), ptr["rgba"], ptr["normal"],
                                      ptr["depth"], ptr["prob"]))
         return res
+
+    def RayCastMerge(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3, merge_ptr: int, n_planes: int = 3):
+        """Sharded grids: raycast with the min-depth merge fused in (rsf_raycast_merge_device).  `merge_ptr` is the
+        device address of the presenting rank's planes (peer memory on the other ranks)."""
+        K, pose = virtual_cam.intrinsics.as_array(), cam_T_world.as_array()
+        _check(self._lib.rsf_raycast_merge_device(self._h, max_depth, virtual_cam.img_h, virtual_cam.img_w, _fptr(K),
+                                                  _fptr(pose), merge_ptr, n_planes))
+
+    def MergeFinalize(self, H: int, W: int, merge_ptr: int, n_planes: int, out: dict):
+        """Presenting rank: unpack the merged planes into the torch CUDA tensors of `out` and re-arm the planes."""
+        ptr = {k: (out[k].data_ptr() if k in out else None) for k in ("rgba", "normal", "depth", "prob")}
+        _check(self._lib.rsf_merge_finalize_device(self._h, H, W, merge_ptr, n_planes, ptr["rgba"], ptr["normal"],
+                                                   ptr["depth"], ptr["prob"]))
+        return out
 
     def synchronize(self):
         _check(self._lib.rsf_synchronize(self._h))

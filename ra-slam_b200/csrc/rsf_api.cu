@@ -330,7 +330,7 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   }
   ok = ok && cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-  A((void**)&g->d_ranges, (P / 256 + 4096) * 2 * sizeof(unsigned) + 64);
+  A((void**)&g->d_ranges, (P / 16 + 4096) * 4 * sizeof(unsigned) + 64);   // tiles <= ceil(W/16) ceil(H/16) <= P/16 + ... for any aspect ratio
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   if (ok) {
     // key = kEmptyKey (all ones), val = kValFree (-1)
@@ -433,6 +433,34 @@ int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float 
     launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, reinterpret_cast<uchar4*>(rgba),
                    reinterpret_cast<uchar4*>(normal), depth, prob, g->sm_count, g->stream);
   }
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+int rsf_raycast_merge_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
+                             uint64_t* merge_planes, int n_planes) {
+  if (int rc = check_grid(g)) return rc;
+  if (!merge_planes || n_planes < 1 || n_planes > 3) return fail(RSF_ERR_INVALID, "merge_planes must be non-NULL, 1 <= n_planes <= 3");
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  {
+    ProfScope p(g, RSF_PROF_RAYCAST);
+    launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, nullptr, nullptr, nullptr, nullptr, g->sm_count, g->stream,
+                   reinterpret_cast<unsigned long long*>(merge_planes), n_planes);
+  }
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+int rsf_merge_finalize_device(rsf_grid_t g, int H, int W, uint64_t* merge_planes, int n_planes, uint8_t* rgba, uint8_t* normal,
+                              float* depth, float* prob) {
+  if (int rc = check_grid(g)) return rc;
+  if (!merge_planes || n_planes < 1 || n_planes > 3 || H <= 0 || W <= 0)
+    return fail(RSF_ERR_INVALID, "merge_planes must be non-NULL, 1 <= n_planes <= 3, H, W > 0");
+  DeviceGuard dg(g->device);
+  launch_merge_finalize(reinterpret_cast<unsigned long long*>(merge_planes), n_planes, H * W, reinterpret_cast<uchar4*>(rgba),
+                        reinterpret_cast<uchar4*>(normal), depth, prob, g->sm_count, g->stream);
   RSF_CUDA(cudaGetLastError());
   return RSF_OK;
 }

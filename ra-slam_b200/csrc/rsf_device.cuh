@@ -195,24 +195,38 @@ __host__ __device__ inline uint32_t mix32(uint32_t h) {
   h ^= h >> 16;
   return h;
 }
-__host__ __device__ inline uint32_t shard_owner(S3 b, int shift, int world) {
-  const int x = b.x >> shift, y = b.y >> shift, z = b.z >> shift;
+__host__ __device__ inline uint32_t shard_owner_brick(int x, int y, int z, int world) {
   const uint32_t h =
       mix32((uint32_t)x * 0x9e3779b1u ^ mix32((uint32_t)y * 0x85ebca77u ^ mix32((uint32_t)z * 0xc2b2ae3du)));
   return h % (uint32_t)world;
 }
+__host__ __device__ inline uint32_t shard_owner(S3 b, int shift, int world) {
+  return shard_owner_brick(b.x >> shift, b.y >> shift, b.z >> shift, world);
+}
 __host__ __device__ inline bool shard_owned(const ShardSpec& s, S3 b) {
   return s.world <= 1 || (int)shard_owner(b, s.shift, s.world) == s.rank;
 }
-// owned, or within `halo` blocks of a block this rank owns
+// owned, or within `halo` blocks of a block this rank owns.  The (2 halo + 1)^3 neighbours fall into at most
+// 2 x 2 x 2 distinct super-bricks (halo < brick size), a single one for the (1 - 2 halo / 2^shift)^3 of blocks in
+// a brick's interior: test the bricks, not the 27 neighbours.
 __host__ __device__ inline bool shard_wanted(const ShardSpec& s, S3 b) {
   if (s.world <= 1) return true;
-  for (int dz = -s.halo; dz <= s.halo; ++dz)
-    for (int dy = -s.halo; dy <= s.halo; ++dy)
-      for (int dx = -s.halo; dx <= s.halo; ++dx) {
-        const S3 n{(short)(b.x + dx), (short)(b.y + dy), (short)(b.z + dz)};
-        if ((int)shard_owner(n, s.shift, s.world) == s.rank) return true;
-      }
+  const int x0 = (short)(b.x - s.halo) >> s.shift, x1 = (short)(b.x + s.halo) >> s.shift;
+  const int y0 = (short)(b.y - s.halo) >> s.shift, y1 = (short)(b.y + s.halo) >> s.shift;
+  const int z0 = (short)(b.z - s.halo) >> s.shift, z1 = (short)(b.z + s.halo) >> s.shift;
+  if ((1 << s.shift) <= 2 * s.halo || x1 < x0 || y1 < y0 || z1 < z0) {   // tiny bricks or int16 wrap-around: brute force
+    for (int dz = -s.halo; dz <= s.halo; ++dz)
+      for (int dy = -s.halo; dy <= s.halo; ++dy)
+        for (int dx = -s.halo; dx <= s.halo; ++dx) {
+          const S3 n{(short)(b.x + dx), (short)(b.y + dy), (short)(b.z + dz)};
+          if ((int)shard_owner(n, s.shift, s.world) == s.rank) return true;
+        }
+    return false;
+  }
+  for (int z = z0; z <= z1; ++z)
+    for (int y = y0; y <= y1; ++y)
+      for (int x = x0; x <= x1; ++x)
+        if ((int)shard_owner_brick(x, y, z, s.world) == s.rank) return true;
   return false;
 }
 

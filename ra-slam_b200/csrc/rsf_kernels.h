@@ -13,8 +13,12 @@ void launch_allocate(const GridView& g, const Frame& f, const uint8_t* rgb, cons
 void launch_select_visible(const GridView& g, const Frame& f, int sm_count, cudaStream_t s);
 void launch_integrate(const GridView& g, const Frame& f, const FramePixel* frame, int sm_count, cudaStream_t s);
 size_t raycast_ranges_bytes(int W, int H);
+// merge != NULL: hits go to the merge planes (depth bits << 32 | payload, system-scope atomicMin) instead of the images
 void launch_raycast(const GridView& g, const Frame& f, float step_size, unsigned* ranges, uchar4* rgba, uchar4* normal,
-                    float* depth, float* prob, int sm_count, cudaStream_t s);
+                    float* depth, float* prob, int sm_count, cudaStream_t s, unsigned long long* merge = nullptr,
+                    int merge_planes = 0);
+void launch_merge_finalize(unsigned long long* merge, int merge_planes, int P, uchar4* rgba, uchar4* normal, float* depth,
+                           float* prob, int sm_count, cudaStream_t s);
 void launch_gather_select(const GridView& g, int mode, int owned_only, S3 lo, S3 hi, int sm_count, cudaStream_t s);
 void launch_download_rows(const GridView& g, float vs, int nblk, int ncol, float* rows, int sm_count, cudaStream_t s);
 void launch_export_blocks(const GridView& g, int nblk, short* coords, float* tsdf, uint32_t* rgbw, float* prob,

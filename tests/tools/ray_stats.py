@@ -4,7 +4,7 @@ import importlib, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-os.environ["RSF_LIBRARY"] = os.path.join(ROOT, "build", "stats", "librsfusion_stats.so")
+os.environ.setdefault("RSF_LIBRARY", os.path.join(ROOT, "build", "stats", "librsfusion_stats.so"))
 rsf = importlib.import_module("ra-slam_b200")
 synth = importlib.import_module("ra-slam_b200.synth")
 seq = synth.config2(n_frames=300, H=480, W=640)
