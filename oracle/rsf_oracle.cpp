@@ -6,10 +6,13 @@
 //
 // Parity status: the hash function, miss defaults, fresh-block defaults and active-block counts
 // are pinned by the reference's own unit tests (utils/tests/voxel_hash_test.cu:130-155,
-// voxel_mem_test.cu:87; see tests/golden/).  Integrate / RayCast / Gather* have NO reference
-// tests or golden vectors and the reference does not build in this image (needs Eigen, OpenCV,
-// GLEW): for those functions **parity is unpinned** -- this file is a line-by-line behavioural
-// restatement of the cited reference code, nothing more.
+// voxel_mem_test.cu:87; see tests/golden/).  Integrate / RayCast / Gather* have no reference
+// tests, so they are pinned by OUTPUT OF THE REFERENCE ITSELF: its unmodified utils/tsdf/*.cu are
+// compiled for sm_100a against stand-in Eigen / OpenCV / GL headers (oracle/Makefile target _ref,
+// oracle/ref_shim/), run on a B200, and tests/golden/reference_small.npz holds what they produced;
+// tests/test_reference_golden.py checks this file against it on CPU (identical block sets and
+// labels, |dTSDF| <= 1e-4 apart from pixel-rounding-tie voxels).  tests/test_gpu_vs_reference.py
+// does the same for the product against the live reference library at full resolution.
 //
 // Arithmetic contract: every float operation is rounded individually (build with
 // -ffp-contract=off, no -ffast-math), in the order the reference source writes it.  Eigen 3.3.7
