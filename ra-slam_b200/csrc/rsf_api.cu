@@ -68,6 +68,8 @@ struct rsf_grid_s {
   // serially on one stream, voxel_tsdf.cu:433-451).
   static constexpr int kSlots = 2;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_side = nullptr;                      // select_visible runs here, next to allocate
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   struct InSlot {
     uint8_t* rgb = nullptr;
     float *depth = nullptr, *ht = nullptr, *lt = nullptr;
@@ -144,7 +146,8 @@ int sync_counters(rsf_grid_t g) {
 struct ProfScope {
   rsf_grid_t g;
   cudaEvent_t stop = nullptr;
-  ProfScope(rsf_grid_t grid, int which) : g(grid) {
+  cudaStream_t st;
+  ProfScope(rsf_grid_t grid, int which, cudaStream_t on = nullptr) : g(grid), st(on ? on : grid->stream) {
     if (!g->profiling) return;
     auto& v = g->prof_events[which];
     size_t& used = g->prof_used[which];
@@ -153,28 +156,36 @@ struct ProfScope {
       if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
       v.emplace_back(a, b);
     }
-    cudaEventRecord(v[used].first, g->stream);
+    cudaEventRecord(v[used].first, st);
     stop = v[used].second;
     ++used;
   }
   ~ProfScope() {
-    if (stop) cudaEventRecord(stop, g->stream);
+    if (stop) cudaEventRecord(stop, st);
   }
 };
 
 int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
                       const float* lt, cudaEvent_t inputs_consumed = nullptr) {
   launch_begin_frame(g->view, g->stream);
+  // allocate (pixels -> new blocks, appended to the visible list as *fresh*) and select_visible (blocks that were
+  // alive before this frame -> visible list) are independent: select skips every slot that is dead or fresh, and a
+  // pool slot only ever goes dead -> fresh during allocate, so it runs on a side stream next to allocate instead of
+  // after it.  Both append through the same atomic counter.
+  RSF_CUDA(cudaEventRecord(g->ev_fork, g->stream));
+  RSF_CUDA(cudaStreamWaitEvent(g->s_side, g->ev_fork, 0));
+  {
+    ProfScope p(g, RSF_PROF_SELECT, g->s_side);
+    launch_select_visible(g->view, f, g->sm_count, g->s_side);
+  }
+  RSF_CUDA(cudaEventRecord(g->ev_join, g->s_side));
   {
     ProfScope p(g, RSF_PROF_ALLOCATE);
     launch_allocate(g->view, f, rgb, depth, ht, lt, g->d_frame, g->stream);
   }
   // the allocate kernel is the only reader of the raw images (it stages them into d_frame)
   if (inputs_consumed) RSF_CUDA(cudaEventRecord(inputs_consumed, g->stream));
-  {
-    ProfScope p(g, RSF_PROF_SELECT);
-    launch_select_visible(g->view, f, g->sm_count, g->stream);
-  }
+  RSF_CUDA(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
   {
     ProfScope p(g, RSF_PROF_INTEGRATE);
     launch_integrate(g->view, f, g->d_frame, g->sm_count, g->stream);
@@ -330,6 +341,9 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   }
   ok = ok && cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming) == cudaSuccess;
   A((void**)&g->d_ranges, (P / 16 + 4096) * 4 * sizeof(unsigned) + 64);   // tiles <= ceil(W/16) ceil(H/16) <= P/16 + ... for any aspect ratio
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   if (ok) {
@@ -354,6 +368,7 @@ int rsf_destroy(rsf_grid_t g) {
   GridView& v = g->view;
   if (g->s_h2d) cudaStreamSynchronize(g->s_h2d);
   if (g->s_d2h) cudaStreamSynchronize(g->s_d2h);
+  if (g->s_side) cudaStreamSynchronize(g->s_side);
   void* ptrs[] = {v.table, v.pool, v.meta, v.heap, v.vis_list, v.gather_list, v.ctr, g->d_frame, g->d_ranges};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -373,6 +388,9 @@ int rsf_destroy(rsf_grid_t g) {
   }
   if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
   if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
+  if (g->s_side) cudaStreamDestroy(g->s_side);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
   for (auto& v : g->prof_events)
     for (auto& e : v) {
