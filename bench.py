@@ -565,6 +565,7 @@ def run_native(args):
                      "updated_voxels_per_launch": upd / max(int_n, 1), "visible_blocks_per_launch": vis / max(int_n, 1),
                      "voxel_updates_per_s": upd / (int_ms * 1e-3) if int_ms else None},
         "kernels": kernels,
+        "kernels_note": "allocate and select_visible run concurrently on two streams, so their two shares overlap",
         "clocks": clocks,
         "map": {"active_blocks": stats_end["active_blocks"], "high_water": stats_end["high_water"]},
     }

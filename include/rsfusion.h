@@ -132,8 +132,9 @@ RSF_API int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, cons
  * kernel (new; the reference is single-GPU).  merge_planes points to n_planes * H * W 64-bit words preset to all-ones --
  * normally the PRESENTING rank's buffer, mapped into this process as NVLink peer memory (torch symmetric memory,
  * cudaIpc, ...).  Every hit this rank owns is one system-scope atomicMin per plane of (depth bits << 32 | payload):
- * plane 0 payload = RGBA8, plane 1 = the normal image, plane 2 = probability bits.  Asynchronous on the grid's stream;
- * no image is written locally. */
+ * plane 0 payload = RGBA8, plane 1 = the normal image, plane 2 = probability bits.  A hit whose refined position has
+ * no positive finite depth (NaN from t_prev == t_curr in the interpolation, voxel_tsdf.cu:327) cannot be ordered and is
+ * dropped.  Asynchronous on the grid's stream; no image is written locally. */
 RSF_API int rsf_raycast_merge_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
                                      uint64_t* merge_planes, int n_planes);
 /* On the presenting rank, after all ranks' rsf_raycast_merge_device kernels have completed (cross-rank barrier):
