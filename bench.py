@@ -296,6 +296,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+DEPTH = 3                 # frames in flight on the pipelined end-to-end path (the library has 4 staging slots)
 SEC_K, SEC_W = 60, 12     # the short secondary measurement (BASELINE.json's metric also names 1296x968)
 
 
@@ -342,7 +343,7 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
             row.append(pa.array)
         h_frames.append(tuple(row))
     h_outs = []
-    for _ in range(2):
+    for _ in range(DEPTH + 1):
         d = {}
         for kname, shape, dt in (("rgba", (H, Wd, 4), np.uint8), ("normal", (H, Wd, 4), np.uint8), ("depth", (H, Wd), np.float32)):
             pa = rsf.PinnedArray(shape, dt)
@@ -354,15 +355,15 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
         grid_e.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    prev = None
+    tickets = []
     for k in range(K):
         i = W + k
         grid_e.IntegrateAsync(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
-        t = grid_e.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k & 1])
-        if prev is not None:
-            grid_e.wait(prev)
-        prev = t
-    grid_e.wait(prev)
+        tickets.append(grid_e.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k % (DEPTH + 1)]))
+        if len(tickets) > DEPTH:
+            grid_e.wait(tickets.pop(0))
+    for t in tickets:
+        grid_e.wait(t)
     grid_e.synchronize()
     e2e_s = time.perf_counter() - t0
     grid_e.close()
@@ -472,7 +473,7 @@ def run_native(args):
             row.append(pa.array)
         h_frames.append(tuple(row))
     h_outs = []
-    for _ in range(2):      # double-buffered read-back targets
+    for _ in range(DEPTH + 1):      # rotating read-back targets
         d = {}
         for kname, shape, dt in (("rgba", (H, Wd, 4), np.uint8), ("normal", (H, Wd, 4), np.uint8), ("depth", (H, Wd), np.float32)):
             pa = rsf.PinnedArray(shape, dt)
@@ -480,7 +481,7 @@ def run_native(args):
             d[kname] = pa.array
         h_outs.append(d)
 
-    # (a) pipelined: rsf_integrate_async + rsf_raycast_async, at most two frames in flight; every step's
+    # (a) pipelined: rsf_integrate_async + rsf_raycast_async, at most DEPTH frames in flight; every step's
     #     H2D and D2H happen inside the timed region and every step's result is waited for
     for i in range(W):
         grid_e.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
@@ -488,19 +489,19 @@ def run_native(args):
     barrier()
     checksum = 0.0
     t0 = time.perf_counter()
-    prev = None
+    tickets = []
     for k in range(K):
         i = W + k
         grid_e.IntegrateAsync(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
-        t = grid_e.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k & 1])
-        if prev is not None:
-            grid_e.wait(prev)
-        prev = t
-    grid_e.wait(prev)
+        tickets.append(grid_e.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k % (DEPTH + 1)]))
+        if len(tickets) > DEPTH:               # every step's result is waited for, DEPTH frames later
+            grid_e.wait(tickets.pop(0))
+    for t in tickets:
+        grid_e.wait(t)
     grid_e.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
-    checksum = float(h_outs[(K - 1) & 1]["depth"].sum())
+    checksum = float(h_outs[(K - 1) % (DEPTH + 1)]["depth"].sum())
     grid_e.close()
 
     # (b) blocking, reference-style calls (rsf_integrate + rsf_raycast return only when done)
@@ -553,8 +554,10 @@ def run_native(args):
         "value_warm_l2": world * K / (warm_ms * 1e-3),
         "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 12 * P,
                 "ms_per_step": 1e3 * e2e_s / K,
-                "api": "rsf_integrate_async + rsf_raycast_async + rsf_wait (3-stream pipeline, <= 2 frames in flight, "
-                       "pinned host buffers)",
+                "api": "rsf_integrate_async + rsf_raycast_async + rsf_wait (3-stream pipeline, <= 3 frames in flight, "
+                       "pinned host buffers; every frame's read-back is waited for)",
+                "l2": "not flushed: a continuous stream, the map (~60 MB) stays L2-resident between frames while every "
+                      "frame's inputs arrive from the host; `value` is the flushed (cold) figure, `value_warm_l2` the warm one",
                 "blocking_value": world / e2e_blocking_s, "blocking_api": "rsf_integrate + rsf_raycast",
                 "checksum": checksum},
         # per frame: begin_frame, allocate, select_visible, integrate, tile_range, raycast

@@ -98,7 +98,7 @@ RSF_API int rsf_destroy(rsf_grid_t g);
 RSF_API int rsf_integrate(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
                   int H, int W, float max_depth, const float K[4], const float pose[7]);
 /* Pipelined form: returns as soon as the copies and kernels are enqueued (H2D on a copy stream,
- * double-buffered, overlapping the kernels of the previous frame).  The host buffers must stay
+ * four staging slots, overlapping the kernels of the previous frames).  The host buffers must stay
  * valid and unchanged until a later rsf_synchronize / rsf_wait on this grid returns; pass
  * page-locked memory (rsf_host_alloc) for true asynchronous DMA.  Device-side errors (pool or table
  * exhaustion) surface at the next rsf_synchronize / blocking call.  This is the path
@@ -119,8 +119,9 @@ RSF_API int rsf_raycast(rsf_grid_t g, float max_depth, int H, int W, const float
                 uint8_t* rgba, uint8_t* normal, float* depth, float* prob);
 /* Pipelined form: kernels on the grid's stream, read-back on a separate D2H stream, double-buffered.
  * *ticket identifies the read-back; the host outputs are valid after rsf_wait(g, ticket) (or
- * rsf_synchronize).  At most two read-backs are in flight: a third call reuses the first ticket's
- * staging and implicitly orders after it. */
+ * rsf_synchronize).  At most four read-backs are in flight: a fifth call reuses the first ticket's
+ * staging and implicitly orders after it (so wait for ticket k before issuing call k + 4, and keep the host
+ * output buffers of a call untouched until its ticket has been waited for). */
 RSF_API int rsf_raycast_async(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
                               uint8_t* rgba, uint8_t* normal, float* depth, float* prob, int* ticket);
 RSF_API int rsf_wait(rsf_grid_t g, int ticket);

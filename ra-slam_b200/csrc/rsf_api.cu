@@ -63,10 +63,10 @@ struct rsf_grid_s {
   size_t table_slots = 0;
   size_t max_pixels = 0;
   // Host entry points run a 3-stage pipeline: H2D on `s_h2d` -> kernels on `stream` -> D2H on
-  // `s_d2h`, chained with events and double-buffered, so the copy of frame k+1 and the read-back
+  // `s_d2h`, chained with events and kSlots-deep, so the copy of frame k+1 and the read-back
   // of frame k-1 overlap the kernels of frame k (the reference copies, computes and reads back
   // serially on one stream, voxel_tsdf.cu:433-451).
-  static constexpr int kSlots = 2;
+  static constexpr int kSlots = 4;   // frames in flight on the pipelined host path (3 hide H2D + compute + D2H latency)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaStream_t s_side = nullptr;                      // select_visible runs here, next to allocate
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
