@@ -367,6 +367,39 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
     grid_e.synchronize()
     e2e_s = time.perf_counter() - t0
     grid_e.close()
+    # (c) the same pipeline fed with the raw 16-bit images the reference's callers convert on the CPU every frame
+    #     (rsf_integrate_u16_async: 9 instead of 15 input bytes per pixel, conversion in the staging kernel)
+    e2e_u16 = None
+    if seq.depth_factor:
+        grid_u = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank)
+        u_frames = []
+        for rgb, depth, ht, lt in frames:
+            row = []
+            for a in (rgb, np.clip(np.rint(depth.astype(np.float64) * seq.depth_factor), 0, 65535).astype(np.uint16),
+                      np.rint(ht.astype(np.float64) * 65535).astype(np.uint16), np.rint(lt.astype(np.float64) * 65535).astype(np.uint16)):
+                pa = rsf.PinnedArray(a.shape, a.dtype)
+                pa.array[...] = a
+                pins.append(pa)
+                row.append(pa.array)
+            u_frames.append(tuple(row))
+        for i in range(W):
+            grid_u.IntegrateU16(*u_frames[i], seq.depth_factor, seq.max_depth, seq.K, seq.poses[i])
+            grid_u.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tickets = []
+        for k in range(K):
+            i = W + k
+            grid_u.IntegrateU16(*u_frames[i], seq.depth_factor, seq.max_depth, seq.K, seq.poses[i], asynchronous=True)
+            tickets.append(grid_u.RayCastAsync(rmax, cam, seq.poses[i], h_outs[k % (DEPTH + 1)]))
+            if len(tickets) > DEPTH:
+                grid_u.wait(tickets.pop(0))
+        for t in tickets:
+            grid_u.wait(t)
+        grid_u.synchronize()
+        e2e_u16 = {"value": K / (time.perf_counter() - t0), "unit": UNIT, "h2d_bytes_per_step": 9 * H * Wd,
+                   "d2h_bytes_per_step": 12 * H * Wd, "api": "rsf_integrate_u16_async + rsf_raycast_async + rsf_wait"}
+        grid_u.close()
     P = H * Wd
     upd = tot1["updated_voxels"] - tot0["updated_voxels"]
     vis = tot1["visible_blocks"] - tot0["visible_blocks"]
@@ -374,6 +407,7 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
     alg = 24.0 * upd + 12.0 * vis + 15.0 * P * int_n
     return {"steps": K, "warmup": W, "unit": UNIT, "value": K / (dev_ms * 1e-3), "ms_per_step": dev_ms / K,
             "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 12 * P},
+            "e2e_u16_inputs": e2e_u16,
             "kernels_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
             "integrate_achieved_gbs": alg / (int_ms * 1e-3) / 1e9 if int_ms else None,
             "updated_voxels_per_launch": upd / max(int_n, 1), "visible_blocks_per_launch": vis / max(int_n, 1)}

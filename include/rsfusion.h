@@ -111,6 +111,24 @@ RSF_API int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* 
                          const float* lt, int H, int W, float max_depth, const float K[4],
                          const float pose[7]);
 
+/* Integrate from the raw 16-bit images (new; GPU-side input preparation).  The reference's callers decode / receive
+ * uint16 depth and uint16 ht / lt images and convert them on the CPU every frame before TSDFGrid::Integrate
+ * (examples/tsdf/offline.cc:62-76: depth.convertTo(CV_32FC1, 1. / depth_scale), ht / lt .convertTo(CV_32FC1, 1. / 65535);
+ * main/offline_eval.cc:74; modules/disinfect_slam.cc:37-40).  Here the conversion happens in the staging kernel with
+ * convertTo's arithmetic, float(raw) * float(1. / factor), so results are identical to converting first and calling
+ * rsf_integrate, 9 instead of 15 bytes per pixel cross PCIe and the host does no per-pixel work.  depth_factor is the
+ * dataset's `depthmap_factor` (raw units per metre).  ht == lt == NULL means "no segmentation": ht = 0, lt = 1
+ * (offline.cc:72-75).  Blocking / pipelined / device-resident forms as for rsf_integrate. */
+RSF_API int rsf_integrate_u16(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht,
+                              const uint16_t* lt, int H, int W, float depth_factor, float max_depth, const float K[4],
+                              const float pose[7]);
+RSF_API int rsf_integrate_u16_async(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht,
+                                    const uint16_t* lt, int H, int W, float depth_factor, float max_depth,
+                                    const float K[4], const float pose[7]);
+RSF_API int rsf_integrate_u16_device(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht,
+                                     const uint16_t* lt, int H, int W, float depth_factor, float max_depth,
+                                     const float K[4], const float pose[7]);
+
 /* TSDFGrid::RayCast (voxel_tsdf.cu:885-902).  rgba / normal are the reference's two RGBA8 images
  * (img_tsdf_rgba_, img_tsdf_normal_); depth (z of the refined hit in the camera frame, 0 = no hit)
  * and prob (fused probability at the hit voxel) are new outputs.  Any output may be NULL.

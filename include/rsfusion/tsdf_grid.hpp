@@ -217,6 +217,16 @@ class TSDFGrid {
     check(rsf_integrate_async(g_, (const uint8_t*)img_rgb.data, (const float*)img_depth.data, (const float*)img_ht.data,
                               (const float*)img_lt.data, img_depth.rows, img_depth.cols, max_depth, K, pose.data()));
   }
+  // Raw 16-bit images (rsf_integrate_u16 / _async): what the reference's callers convert on the CPU before Integrate
+  // (examples/tsdf/offline.cc:62-76).  img_ht / img_lt may both be null pointers ("no segmentation": ht 0, lt 1).
+  void IntegrateU16(const uint8_t* img_rgb, const uint16_t* img_depth, const uint16_t* img_ht, const uint16_t* img_lt, int rows,
+                    int cols, float depth_factor, float max_depth, const CameraIntrinsics<float>& intrinsics,
+                    const SE3<float>& cam_T_world, bool asynchronous = false) {
+    const float K[4] = {intrinsics.fx, intrinsics.fy, intrinsics.cx, intrinsics.cy};
+    const auto pose = cam_T_world.as_pose();
+    check((asynchronous ? rsf_integrate_u16_async : rsf_integrate_u16)(g_, img_rgb, img_depth, img_ht, img_lt, rows, cols,
+                                                                        depth_factor, max_depth, K, pose.data()));
+  }
   void Synchronize() { check(rsf_synchronize(g_)); }
 
   // voxel_tsdf.cu:885-902.  rgba / normal: img_h*img_w*4 bytes each; depth / prob: img_h*img_w floats.

@@ -63,6 +63,9 @@ ABI = {
     "rsf_raycast_async": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P, C.POINTER(C.c_int)]),
     "rsf_wait": (C.c_int, [_P, C.c_int]),
     "rsf_integrate_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
+    "rsf_integrate_u16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F4, _F4]),
+    "rsf_integrate_u16_async": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F4, _F4]),
+    "rsf_integrate_u16_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F4, _F4]),
     "rsf_raycast": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_merge_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, C.c_int]),
@@ -341,6 +344,24 @@ class TSDFGrid:
         K, pose = intrinsics.as_array(), cam_T_world.as_array()
         _check(self._lib.rsf_integrate_async(self._h, img_rgb.ctypes.data, img_depth.ctypes.data, img_ht.ctypes.data,
                                              img_lt.ctypes.data, H, W, max_depth, _fptr(K), _fptr(pose)))
+
+    def IntegrateU16(self, img_rgb, depth_u16, ht_u16, lt_u16, depth_factor: float, max_depth: float,
+                     intrinsics: CameraIntrinsics, cam_T_world: SE3, *, asynchronous: bool = False):
+        """Integrate from raw 16-bit depth / ht / lt images (rsf_integrate_u16*): numpy arrays (host; blocking or
+        `asynchronous`) or torch CUDA tensors (device).  ht_u16 = lt_u16 = None means "no segmentation"."""
+        H, W = depth_u16.shape
+        K, pose = intrinsics.as_array(), cam_T_world.as_array()
+        if _is_torch_cuda(depth_u16):
+            ptrs = [img_rgb.data_ptr(), depth_u16.data_ptr(), ht_u16.data_ptr() if ht_u16 is not None else None,
+                    lt_u16.data_ptr() if lt_u16 is not None else None]
+            fn = self._lib.rsf_integrate_u16_device
+        else:
+            assert img_rgb.dtype == np.uint8 and depth_u16.dtype == np.uint16
+            assert all(a.flags["C_CONTIGUOUS"] for a in (img_rgb, depth_u16))
+            ptrs = [img_rgb.ctypes.data, depth_u16.ctypes.data, ht_u16.ctypes.data if ht_u16 is not None else None,
+                    lt_u16.ctypes.data if lt_u16 is not None else None]
+            fn = self._lib.rsf_integrate_u16_async if asynchronous else self._lib.rsf_integrate_u16
+        _check(fn(self._h, *ptrs, H, W, depth_factor, max_depth, _fptr(K), _fptr(pose)))
 
     def RayCastAsync(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3, out: dict) -> int:
         """Enqueue raycast + read-back into the numpy arrays of `out`; returns a ticket for `wait`."""

@@ -165,8 +165,10 @@ struct ProfScope {
   }
 };
 
-int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
-                      const float* lt, cudaEvent_t inputs_consumed = nullptr) {
+// u16 = true: depth / ht / lt point to uint16 images, converted in the allocate kernel with the two scale factors
+int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const void* depth, const void* ht,
+                      const void* lt, cudaEvent_t inputs_consumed = nullptr, bool u16 = false, float depth_alpha = 1.f,
+                      float prob_alpha = 1.f) {
   launch_begin_frame(g->view, g->stream);
   // allocate (pixels -> new blocks, appended to the visible list as *fresh*) and select_visible (blocks that were
   // alive before this frame -> visible list) are independent: select skips every slot that is dead or fresh, and a
@@ -181,7 +183,11 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const fl
   RSF_CUDA(cudaEventRecord(g->ev_join, g->s_side));
   {
     ProfScope p(g, RSF_PROF_ALLOCATE);
-    launch_allocate(g->view, f, rgb, depth, ht, lt, g->d_frame, g->stream);
+    if (u16)
+      launch_allocate_u16(g->view, f, rgb, (const uint16_t*)depth, (const uint16_t*)ht, (const uint16_t*)lt, depth_alpha,
+                          prob_alpha, g->d_frame, g->stream);
+    else
+      launch_allocate(g->view, f, rgb, (const float*)depth, (const float*)ht, (const float*)lt, g->d_frame, g->stream);
   }
   // the allocate kernel is the only reader of the raw images (it stages them into d_frame)
   if (inputs_consumed) RSF_CUDA(cudaEventRecord(inputs_consumed, g->stream));
@@ -437,6 +443,52 @@ int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, c
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
   return enqueue_integrate(g, f, rgb, depth, ht, lt);
+}
+
+// cv::Mat::convertTo(CV_32FC1, alpha) multiplies in float: alpha = float(1. / factor)
+static inline float u16_alpha(float factor) { return (float)(1.0 / (double)factor); }
+
+int rsf_integrate_u16_async(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht, const uint16_t* lt,
+                            int H, int W, float depth_factor, float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!rgb || !depth || ((ht == nullptr) != (lt == nullptr)))
+    return fail(RSF_ERR_INVALID, "rgb / depth must not be NULL; ht and lt must be given together or both be NULL");
+  if (!(depth_factor > 0.f)) return fail(RSF_ERR_INVALID, "depth_factor must be > 0");
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  const size_t P = (size_t)H * W;
+  auto& sl = g->in[g->in_next++ % rsf_grid_s::kSlots];
+  RSF_CUDA(cudaStreamWaitEvent(g->s_h2d, sl.free_, 0));
+  RSF_CUDA(cudaMemcpyAsync(sl.depth, depth, P * sizeof(uint16_t), cudaMemcpyHostToDevice, g->s_h2d));
+  RSF_CUDA(cudaMemcpyAsync(sl.rgb, rgb, P * 3, cudaMemcpyHostToDevice, g->s_h2d));
+  if (ht) {
+    RSF_CUDA(cudaMemcpyAsync(sl.ht, ht, P * sizeof(uint16_t), cudaMemcpyHostToDevice, g->s_h2d));
+    RSF_CUDA(cudaMemcpyAsync(sl.lt, lt, P * sizeof(uint16_t), cudaMemcpyHostToDevice, g->s_h2d));
+  }
+  RSF_CUDA(cudaEventRecord(sl.ready, g->s_h2d));
+  RSF_CUDA(cudaStreamWaitEvent(g->stream, sl.ready, 0));
+  return enqueue_integrate(g, f, sl.rgb, sl.depth, ht ? sl.ht : nullptr, ht ? sl.lt : nullptr, sl.free_, true,
+                           u16_alpha(depth_factor), u16_alpha(65535.f));
+}
+
+int rsf_integrate_u16(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht, const uint16_t* lt, int H,
+                      int W, float depth_factor, float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = rsf_integrate_u16_async(g, rgb, depth, ht, lt, H, W, depth_factor, max_depth, K, pose)) return rc;
+  DeviceGuard dg(g->device);
+  return sync_counters(g);
+}
+
+int rsf_integrate_u16_device(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht, const uint16_t* lt,
+                             int H, int W, float depth_factor, float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!rgb || !depth || ((ht == nullptr) != (lt == nullptr)))
+    return fail(RSF_ERR_INVALID, "rgb / depth must not be NULL; ht and lt must be given together or both be NULL");
+  if (!(depth_factor > 0.f)) return fail(RSF_ERR_INVALID, "depth_factor must be > 0");
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  return enqueue_integrate(g, f, rgb, depth, ht, lt, nullptr, true, u16_alpha(depth_factor), u16_alpha(65535.f));
 }
 
 int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,

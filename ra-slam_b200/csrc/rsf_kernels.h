@@ -10,6 +10,8 @@ void launch_init_pool(const GridView& g, cudaStream_t s);
 void launch_begin_frame(const GridView& g, cudaStream_t s);
 void launch_allocate(const GridView& g, const Frame& f, const uint8_t* rgb, const float* depth, const float* ht,
                      const float* lt, FramePixel* frame, cudaStream_t s);
+void launch_allocate_u16(const GridView& g, const Frame& f, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht,
+                         const uint16_t* lt, float depth_alpha, float prob_alpha, FramePixel* frame, cudaStream_t s);
 void launch_select_visible(const GridView& g, const Frame& f, int sm_count, cudaStream_t s);
 void launch_integrate(const GridView& g, const Frame& f, const FramePixel* frame, int sm_count, cudaStream_t s);
 size_t raycast_ranges_bytes(int W, int H);

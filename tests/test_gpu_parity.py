@@ -403,3 +403,35 @@ def test_fused_merge_equals_plain_raycast(rsf, synth):
     assert same.mean() >= 0.99                                   # the march is stateful across shard borders
     assert (np.abs(got["depth"][both] - ref["depth"][both]) <= 0.5 * seq.voxel_size).mean() >= 0.998
     assert np.array_equal(got["rgba"][both][same], ref["rgba"][both][same])
+
+
+# ---- raw 16-bit inputs (rsf_integrate_u16*): GPU-side input preparation --------------------------------------
+def test_integrate_u16_equals_converted_float_path(rsf, synth):
+    """depth / ht / lt as uint16 images converted in the staging kernel == cv::Mat::convertTo on the CPU followed by the
+    float entry point (examples/tsdf/offline.cc:62-76), bit for bit; and ht = lt = NULL means ht 0 / lt 1."""
+    seq = synth.config2(n_frames=300, H=120, W=160)
+    factor = 5000.0
+    a = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    b = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    c = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    d = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
+    for i in range(12):
+        rgb, depth, ht, lt = seq.frame(i)
+        d16 = np.clip(np.rint(depth.astype(np.float64) * factor), 0, 65535).astype(np.uint16)
+        h16 = np.clip(np.rint(ht.astype(np.float64) * 65535), 0, 65535).astype(np.uint16)
+        l16 = np.clip(np.rint(lt.astype(np.float64) * 65535), 0, 65535).astype(np.uint16)
+        # what the reference's callers do on the CPU (convertTo multiplies in float)
+        df = d16.astype(np.float32) * np.float32(1.0 / factor)
+        hf = h16.astype(np.float32) * np.float32(1.0 / 65535)
+        lf = l16.astype(np.float32) * np.float32(1.0 / 65535)
+        a.Integrate(rgb, df, hf, lf, seq.max_depth, seq.K, seq.poses[i])
+        b.IntegrateU16(rgb, d16, h16, l16, factor, seq.max_depth, seq.K, seq.poses[i])
+        c.Integrate(rgb, df, np.zeros_like(df), np.ones_like(df), seq.max_depth, seq.K, seq.poses[i])
+        d.IntegrateU16(rgb, d16, None, None, factor, seq.max_depth, seq.K, seq.poses[i], asynchronous=True)
+    d.synchronize()
+    for x, y in ((a, b), (c, d)):
+        ex, ey = x.ExportBlocks(), y.ExportBlocks()
+        assert np.array_equal(ex[0], ey[0]) and len(ex[0]) > 1000
+        assert np.array_equal(ex[1].view(np.uint32), ey[1].view(np.uint32))
+        assert np.array_equal(ex[2], ey[2])
+        assert np.array_equal(ex[3].view(np.uint32), ey[3].view(np.uint32))

@@ -126,3 +126,30 @@ def test_sharded_fusion_merges_to_single_grid_over_gloo(synth, rsf):
     for k in ("rgba", "normal", "prob"):
         assert np.array_equal(merged[k][valid][same], ref[k][valid][same]), k
     assert (merged["rgba"][~valid] == 0).all()
+
+
+def test_folder_dataset_and_dump_formats(tmp_path, synth):
+    """The reference's folder dataset (folder_reader.cc / offline.cc) and its evaluation dumps, round trip."""
+    import importlib
+    fmt = importlib.import_module("ra-slam_b200.formats")
+    seq = synth.config2(n_frames=300, H=48, W=64)
+    frames = [seq.frame(i) for i in range(3)]
+    fmt.FolderDataset.write(str(tmp_path / "ds"), seq.K, 5000.0, frames, seq.poses[:3], ids=[7, 8, 12])
+    ds = fmt.FolderDataset(str(tmp_path / "ds"))
+    assert len(ds) == 3 and [e[0] for e in ds.entries] == [7, 8, 12] and ds.depth_factor == 5000.0
+    assert abs(ds.intrinsics.fx - seq.K.fx) < 1e-4
+    for i in range(3):
+        rgb, depth, ht, lt = ds.frame(i)
+        assert np.array_equal(rgb, frames[i][0])
+        assert np.abs(depth - frames[i][1]).max() <= 0.5 / 5000 + 1e-6        # uint16 quantisation
+        assert np.abs(ht - frames[i][2]).max() <= 1.0 / 65535 and np.abs(lt - frames[i][3]).max() <= 1.0 / 65535
+        raw = ds.raw(i)
+        assert raw[1].dtype == np.uint16 and raw[2].dtype == np.uint16
+        assert np.allclose(ds.pose(i).matrix(), seq.poses[i].matrix(), atol=1e-6)
+    rows = np.random.default_rng(0).normal(size=(100, 5)).astype(np.float32)
+    fmt.write_semantic_bin(str(tmp_path / "tsdf.bin"), rows)
+    assert os.path.getsize(tmp_path / "tsdf.bin") == 100 * 20 and np.array_equal(fmt.read_semantic_bin(str(tmp_path / "tsdf.bin")), rows)
+    v, t, p = rows[:, :3], np.arange(30, dtype=np.int32).reshape(10, 3), rows[:, 4]
+    fmt.write_mesh_bins(str(tmp_path / "mesh"), v, t, p)
+    v2, t2, p2 = fmt.read_mesh_bins(str(tmp_path / "mesh"))
+    assert np.array_equal(v, v2) and np.array_equal(t, t2) and np.array_equal(p, p2)
