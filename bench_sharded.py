@@ -109,19 +109,28 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     grid.profile_enable(True)
+    # headline: K steps with only the two step events (per-phase events cost ~40 us of host time per step, which shows
+    # up as GPU idle time because every phase is a handful of short launches)
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
-        step(W + k, timed=True)
+        step(W + k)
         ev[k][1].record()
     barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     prof = grid.profile_read()
-    phases = {}
-    for name, a, b in phase_ev:
-        phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
     tot1 = grid.totals()
     st = grid.stats()
+    # breakdown: the last frames again (map already built: steady state), with per-phase events; not with --verify,
+    # which compares the map against an unsharded grid that only sees every frame once
+    Kd = 0 if args.verify else min(K, 16)
+    for k in range(Kd):
+        flush.zero_()
+        step(W + K - Kd + k, timed=True)
+    barrier()
+    phases = {}
+    for name, a, b in phase_ev:
+        phases[name] = phases.get(name, 0.0) + a.elapsed_time(b) * (K / Kd)
     vals = torch.tensor([ms, float(tot1["updated_voxels"] - tot0["updated_voxels"]), float(st["active_blocks"]),
                          float(tot1["visible_blocks"] - tot0["visible_blocks"])], dtype=torch.float64, device=dev)
     mx = vals.clone()
@@ -129,6 +138,15 @@ def main():
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    # per-rank kernel times (load balance across shards)
+    mine = torch.tensor([(prof[k][0] / prof[k][1] if prof[k][1] else 0.0) for k in ("allocate", "select", "integrate", "raycast")],
+                        dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [[round(float(x), 4) for x in t.tolist()] for t in per_rank]
     verify = None
     if args.verify:
         owned = grid.ExportBlocks(owned_only=True)[0]
@@ -167,6 +185,7 @@ def main():
                 "visible_blocks_per_step_max_rank": float(mx[3]) / K,
                 "rank0_phase_ms_per_step": {k: v / K for k, v in phases.items()},
                 "rank0_kernel_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
+                "per_rank_kernel_ms_per_launch[allocate,select,integrate,raycast]": per_rank,
                 "verify": verify}
         print(json.dumps(line), flush=True)
     if world > 1:
