@@ -71,6 +71,9 @@ typedef struct rsf_options {
   int shard_halo;          /*   redundant halo in blocks; default 1                         */
   void* stream;            /* optional external cudaStream_t; NULL = library-owned stream   */
   unsigned flags;          /* RSF_FLAG_* bits                                               */
+  int num_classes;         /* K-class semantic extension: 0 / 2 = the reference's ht / lt only;   */
+                           /*   3..64 adds a pool of K log-probability planes per block            */
+                           /*   (pool_blocks * K * 2 KiB) and enables rsf_integrate_classes*       */
 } rsf_options;
 
 /* Per-frame counters of the last rsf_integrate* call (reference logs only block counts,
@@ -128,6 +131,21 @@ RSF_API int rsf_integrate_u16_async(rsf_grid_t g, const uint8_t* rgb, const uint
 RSF_API int rsf_integrate_u16_device(rsf_grid_t g, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht,
                                      const uint16_t* lt, int H, int W, float depth_factor, float max_depth,
                                      const float K[4], const float pose[7]);
+
+/* K-class semantic fusion (extension; rsf_options.num_classes = K > 2).  The reference fuses two planes, ht and lt
+ * (voxel_tsdf.cu:241-248); its K-class form is
+ *   p_k <- exp((w_old ln p_k + w_new ln q_k) / w) / sum_j exp((w_old ln p_j + w_new ln q_j) / w)
+ * with the same w_old / w_new and the same update decision as the TSDF update.  class_prob: K planes of H*W f32
+ * probabilities (q_k > 0).  Everything else (allocation, TSDF, weight, colour, carving) is exactly rsf_integrate; the binary
+ * ht / lt channel is fed ht = lt and therefore keeps its prior.  _device: device pointers, asynchronous on the grid's
+ * stream; the other form takes host pointers and blocks. */
+RSF_API int rsf_integrate_classes_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* class_prob, int H,
+                                         int W, float max_depth, const float K[4], const float pose[7]);
+RSF_API int rsf_integrate_classes(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* class_prob, int H, int W,
+                                  float max_depth, const float K[4], const float pose[7]);
+/* K-class counterpart of GatherValidSemantic: rows of 4 + K f32 (x, y, z, tsdf, p_0 .. p_{K-1}), probabilities normalised
+ * (uniform 1/K for never-updated voxels).  Size query with rows == NULL. */
+RSF_API int rsf_gather_valid_classes(rsf_grid_t g, float* rows, int64_t cap_rows, int64_t* n_rows);
 
 /* TSDFGrid::RayCast (voxel_tsdf.cu:885-902).  rgba / normal are the reference's two RGBA8 images
  * (img_tsdf_rgba_, img_tsdf_normal_); depth (z of the refined hit in the camera frame, 0 = no hit)

@@ -127,6 +127,7 @@ struct Block {
   float tsdf[kBlockVol];
   uint8_t rgbw[kBlockVol * 4];   // r,g,b,weight  (voxel_types.cuh:10-19)
   float prob[kBlockVol];
+  std::vector<float> cls;        // K-class extension: normalised probabilities [k][voxel], empty when K <= 2
   void reset() {                                       // voxel_mem.cu:44-51 (rgb: undefined -> 0)
     for (int i = 0; i < kBlockVol; ++i) {
       tsdf[i] = -1.f;
@@ -164,6 +165,9 @@ struct Grid {
   Stats stats{};
   // sharding
   int shard_rank = 0, shard_world = 1, shard_shift = 4, shard_halo = 1;
+  // K-class semantic extension: per-class probability planes of the current frame
+  int num_classes = 0;
+  const float* cls_in = nullptr;     // [K][H*W]
 
   bool wanted(S3 b) const {
     if (shard_world <= 1) return true;
@@ -273,6 +277,7 @@ void allocate(Grid& g, const float* depth, int H, int W, float max_depth, const 
         slot.reset(new Block);
         slot->pos = unpack(key);
         slot->reset();
+        if (g.num_classes > 2) slot->cls.assign((size_t)g.num_classes * kBlockVol, 1.f / (float)g.num_classes);
         ++n_new;
       }
     }
@@ -308,6 +313,20 @@ int integrate_block(Block& B, const Grid& g, const uint8_t* rgb, const float* de
         for (int c = 0; c < 3; ++c) {
           const float o = (float)B.rgbw[4 * i + c], nw = (float)rgb[3 * pi + c];
           B.rgbw[4 * i + c] = (uint8_t)(int)std::round((o * wo + nw * wn) / w);
+        }
+        if (g.cls_in) {
+          // K-class form of voxel_tsdf.cu:241-248:
+          //   p_k <- exp((w_old ln p_k + w_new ln q_k) / w) / sum_j exp((w_old ln p_j + w_new ln q_j) / w)
+          const int Kc = g.num_classes;
+          const size_t P = (size_t)H * W;
+          if (B.cls.empty()) B.cls.assign((size_t)Kc * kBlockVol, 1.f / (float)Kc);   // block made by a test hook
+          float sum = 0.f;
+          for (int k = 0; k < Kc; ++k) {
+            float& pk = B.cls[(size_t)k * kBlockVol + i];
+            pk = std::exp((wo * std::log(pk) + wn * std::log(g.cls_in[(size_t)k * P + pi])) / w);
+            sum += pk;
+          }
+          for (int k = 0; k < Kc; ++k) B.cls[(size_t)k * kBlockVol + i] /= sum;
         }
         B.tsdf[i] = (B.tsdf[i] * wo + tn * wn) / w;
         B.rgbw[4 * i + 3] = (uint8_t)(int)std::fmin(std::round(w), 40.f);
@@ -534,6 +553,33 @@ static SE3 pose_of(const float* p) { return SE3{Quat{p[0], p[1], p[2], p[3]}, V3
 void ora_integrate(ora_grid* o, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H, int W,
                    float max_depth, const float* K, const float* pose) {
   integrate(o->g, rgb, depth, ht, lt, H, W, max_depth, Intr{K[0], K[1], K[2], K[3]}, pose_of(pose));
+}
+// K-class extension: class_prob = [K][H*W] per-class probabilities of the frame.  The binary ht / lt channel sees
+// ht = lt = plane 0, i.e. stays at its prior, exactly as the product's rsf_integrate_classes* does.
+void ora_integrate_classes(ora_grid* o, const uint8_t* rgb, const float* depth, const float* class_prob, int num_classes,
+                           int H, int W, float max_depth, const float* K, const float* pose) {
+  o->g.num_classes = num_classes;
+  o->g.cls_in = class_prob;
+  integrate(o->g, rgb, depth, class_prob, class_prob, H, W, max_depth, Intr{K[0], K[1], K[2], K[3]}, pose_of(pose));
+  o->g.cls_in = nullptr;
+}
+// rows (x, y, z, tsdf, p_0 .. p_{K-1}); block order = sorted key order; rows may be NULL to size
+int64_t ora_gather_valid_classes(ora_grid* o, float* rows) {
+  const Grid& g = o->g;
+  const int Kc = g.num_classes, nc = 4 + Kc;
+  const auto v = sorted_blocks(g);
+  if (rows)
+    for (size_t bi = 0; bi < v.size(); ++bi)
+      for (int i = 0; i < kBlockVol; ++i) {
+        const int ox = i & 7, oy = (i >> 3) & 7, oz = i >> 6;
+        float* r = rows + (bi * kBlockVol + i) * nc;
+        r[0] = (float)(int16_t)((v[bi]->pos.x << 3) + ox) * g.vs;
+        r[1] = (float)(int16_t)((v[bi]->pos.y << 3) + oy) * g.vs;
+        r[2] = (float)(int16_t)((v[bi]->pos.z << 3) + oz) * g.vs;
+        r[3] = v[bi]->tsdf[i];
+        for (int k = 0; k < Kc; ++k) r[4 + k] = v[bi]->cls.empty() ? 1.f / (float)Kc : v[bi]->cls[(size_t)k * kBlockVol + i];
+      }
+  return (int64_t)v.size() * kBlockVol;
 }
 void ora_raycast(ora_grid* o, float max_depth, int H, int W, const float* K, const float* pose, uint8_t* rgba,
                  uint8_t* normal, float* depth, float* prob) {

@@ -40,7 +40,7 @@ class rsf_options(C.Structure):
         ("voxel_size", C.c_float), ("truncation", C.c_float), ("device", C.c_int),
         ("pool_blocks", C.c_int), ("table_slots_log2", C.c_int), ("max_pixels", C.c_int),
         ("shard_rank", C.c_int), ("shard_world", C.c_int), ("shard_shift", C.c_int),
-        ("shard_halo", C.c_int), ("stream", C.c_void_p), ("flags", C.c_uint),
+        ("shard_halo", C.c_int), ("stream", C.c_void_p), ("flags", C.c_uint), ("num_classes", C.c_int),
     ]
 
 
@@ -66,6 +66,9 @@ ABI = {
     "rsf_integrate_u16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F4, _F4]),
     "rsf_integrate_u16_async": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F4, _F4]),
     "rsf_integrate_u16_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, _F4, _F4]),
+    "rsf_integrate_classes": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
+    "rsf_integrate_classes_device": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
+    "rsf_gather_valid_classes": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "rsf_raycast": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_merge_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, C.c_int]),
@@ -244,13 +247,15 @@ class TSDFGrid:
 
     def __init__(self, voxel_size: float, truncation: float, *, device: int = -1, pool_blocks: int = 0,
                  table_slots_log2: int = 0, max_pixels: int = 0, shard_rank: int = 0, shard_world: int = 1,
-                 shard_shift: int = 4, shard_halo: int = 1, stream: int | None = None):
+                 shard_shift: int = 4, shard_halo: int = 1, stream: int | None = None, num_classes: int = 0):
         self._lib = load_library()
         o = rsf_options()
         self._lib.rsf_default_options(C.byref(o))
         o.voxel_size, o.truncation, o.device = voxel_size, truncation, device
         o.pool_blocks, o.table_slots_log2, o.max_pixels = pool_blocks, table_slots_log2, max_pixels
         o.shard_rank, o.shard_world, o.shard_shift, o.shard_halo = shard_rank, shard_world, shard_shift, shard_halo
+        o.num_classes = num_classes
+        self.num_classes = num_classes
         if stream is not None:
             o.stream = stream or None
             o.flags = 1          # RSF_FLAG_EXTERNAL_STREAM: use it even if it is the default stream (0)
@@ -317,6 +322,25 @@ class TSDFGrid:
         _check(self._lib.rsf_raycast(self._h, max_depth, H, W, _fptr(K), _fptr(pose), ptr["rgba"], ptr["normal"],
                                      ptr["depth"], ptr["prob"]))
         return res
+
+    # -- K-class semantic extension (rsf_options.num_classes > 2) ----------------------------------
+    def IntegrateClasses(self, img_rgb, img_depth, class_prob, max_depth: float, intrinsics: CameraIntrinsics, cam_T_world: SE3):
+        """class_prob: K x H x W float32 per-class probabilities (numpy: blocking host path; torch CUDA: device path)."""
+        H, W = img_depth.shape
+        K, pose = intrinsics.as_array(), cam_T_world.as_array()
+        assert tuple(class_prob.shape) == (self.num_classes, H, W)
+        if _is_torch_cuda(img_depth):
+            _check(self._lib.rsf_integrate_classes_device(self._h, img_rgb.data_ptr(), img_depth.data_ptr(), class_prob.data_ptr(),
+                                                          H, W, max_depth, _fptr(K), _fptr(pose)))
+        else:
+            img_rgb, img_depth, class_prob = (np.ascontiguousarray(a) for a in (img_rgb, img_depth, class_prob))
+            assert img_rgb.dtype == np.uint8 and img_depth.dtype == np.float32 and class_prob.dtype == np.float32
+            _check(self._lib.rsf_integrate_classes(self._h, img_rgb.ctypes.data, img_depth.ctypes.data, class_prob.ctypes.data,
+                                                   H, W, max_depth, _fptr(K), _fptr(pose)))
+
+    def GatherValidClasses(self) -> np.ndarray:
+        """N x (4 + K) float32 rows {x, y, z, tsdf, p_0 .. p_{K-1}}."""
+        return self._gather(self._lib.rsf_gather_valid_classes, 4 + self.num_classes)
 
     def RayCastMerge(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3, merge_ptr: int, n_planes: int = 3):
         """Sharded grids: raycast with the min-depth merge fused in (rsf_raycast_merge_device).  `merge_ptr` is the

@@ -85,6 +85,7 @@ struct rsf_grid_s {
   unsigned in_next = 0, out_next = 0;
   float4* d_frame = nullptr;       // staged frame records (written by allocate, read by integrate)
   unsigned* d_ranges = nullptr;   // per-tile depth ranges of the raycast pre-pass
+  float* class_pool = nullptr;    // K-class extension: [pool_blocks][K][512] un-normalised log-probabilities
   // pinned mirror of the device counters
   Counters* h_ctr = nullptr;
   rsf_frame_stats last{};
@@ -168,7 +169,7 @@ struct ProfScope {
 // u16 = true: depth / ht / lt point to uint16 images, converted in the allocate kernel with the two scale factors
 int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const void* depth, const void* ht,
                       const void* lt, cudaEvent_t inputs_consumed = nullptr, bool u16 = false, float depth_alpha = 1.f,
-                      float prob_alpha = 1.f) {
+                      float prob_alpha = 1.f, const float* class_prob = nullptr) {
   launch_begin_frame(g->view, g->stream);
   // allocate (pixels -> new blocks, appended to the visible list as *fresh*) and select_visible (blocks that were
   // alive before this frame -> visible list) are independent: select skips every slot that is dead or fresh, and a
@@ -192,6 +193,9 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const vo
   // the allocate kernel is the only reader of the raw images (it stages them into d_frame)
   if (inputs_consumed) RSF_CUDA(cudaEventRecord(inputs_consumed, g->stream));
   RSF_CUDA(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
+  // K-class extension: the class planes are updated with the weights from BEFORE this frame's TSDF update
+  if (class_prob)
+    launch_class_update(g->view, f, g->d_frame, class_prob, g->opt.num_classes, g->class_pool, g->sm_count, g->stream);
   {
     ProfScope p(g, RSF_PROF_INTEGRATE);
     launch_integrate(g->view, f, g->d_frame, g->sm_count, g->stream);
@@ -284,6 +288,8 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
     return fail(RSF_ERR_INVALID, "table_slots_log2=%d must give >= 2x pool_blocks=%d slots", o.table_slots_log2, o.pool_blocks);
   if (o.shard_rank < 0 || o.shard_rank >= o.shard_world) return fail(RSF_ERR_INVALID, "shard_rank outside [0, shard_world)");
   if (o.flags & ~(unsigned)RSF_FLAG_EXTERNAL_STREAM) return fail(RSF_ERR_INVALID, "unknown bits in flags");
+  if (o.num_classes == 2) o.num_classes = 0;
+  if (o.num_classes != 0 && (o.num_classes < 3 || o.num_classes > 64)) return fail(RSF_ERR_INVALID, "num_classes must be 0, 2 or 3..64");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -351,6 +357,7 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   ok = ok && cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming) == cudaSuccess;
   A((void**)&g->d_ranges, (P / 16 + 4096) * 4 * sizeof(unsigned) + 64);   // tiles <= ceil(W/16) ceil(H/16) <= P/16 + ... for any aspect ratio
+  if (o.num_classes > 2) A((void**)&g->class_pool, (size_t)o.pool_blocks * o.num_classes * kBlockVol * sizeof(float));
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   if (ok) {
     // key = kEmptyKey (all ones), val = kValFree (-1)
@@ -375,7 +382,7 @@ int rsf_destroy(rsf_grid_t g) {
   if (g->s_h2d) cudaStreamSynchronize(g->s_h2d);
   if (g->s_d2h) cudaStreamSynchronize(g->s_d2h);
   if (g->s_side) cudaStreamSynchronize(g->s_side);
-  void* ptrs[] = {v.table, v.pool, v.meta, v.heap, v.vis_list, v.gather_list, v.ctr, g->d_frame, g->d_ranges};
+  void* ptrs[] = {v.table, v.pool, v.meta, v.heap, v.vis_list, v.gather_list, v.ctr, g->d_frame, g->d_ranges, g->class_pool};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& sl : g->in) {
@@ -443,6 +450,62 @@ int rsf_integrate_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, c
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
   return enqueue_integrate(g, f, rgb, depth, ht, lt);
+}
+
+int rsf_integrate_classes_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* class_prob, int H, int W,
+                                 float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!g->class_pool) return fail(RSF_ERR_INVALID, "grid was created without rsf_options.num_classes > 2");
+  if (!rgb || !depth || !class_prob) return fail(RSF_ERR_INVALID, "rgb / depth / class_prob must not be NULL");
+  Frame f;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  DeviceGuard dg(g->device);
+  // binary channel: ht = lt = plane 0 -> ln ht - ln lt = 0, the prior is kept
+  return enqueue_integrate(g, f, rgb, depth, class_prob, class_prob, nullptr, false, 1.f, 1.f, class_prob);
+}
+
+int rsf_integrate_classes(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* class_prob, int H, int W,
+                          float max_depth, const float K[4], const float pose[7]) {
+  if (int rc = check_grid(g)) return rc;
+  if (!g->class_pool) return fail(RSF_ERR_INVALID, "grid was created without rsf_options.num_classes > 2");
+  if (!rgb || !depth || !class_prob) return fail(RSF_ERR_INVALID, "rgb / depth / class_prob must not be NULL");
+  if (H <= 0 || W <= 0 || (size_t)H * (size_t)W > g->max_pixels) return fail(RSF_ERR_INVALID, "image size outside (0, max_pixels]");
+  DeviceGuard dg(g->device);
+  const size_t P = (size_t)H * W;
+  DevBuf<uint8_t> d_rgb(g->stream);
+  DevBuf<float> d_depth(g->stream), d_cls(g->stream);
+  RSF_CUDA(d_rgb.alloc(P * 3));
+  RSF_CUDA(d_depth.alloc(P));
+  RSF_CUDA(d_cls.alloc(P * g->opt.num_classes));
+  RSF_CUDA(cudaMemcpyAsync(d_rgb.p, rgb, P * 3, cudaMemcpyHostToDevice, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(d_depth.p, depth, P * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  RSF_CUDA(cudaMemcpyAsync(d_cls.p, class_prob, P * g->opt.num_classes * sizeof(float), cudaMemcpyHostToDevice, g->stream));
+  if (int rc = rsf_integrate_classes_device(g, d_rgb.p, d_depth.p, d_cls.p, H, W, max_depth, K, pose)) return rc;
+  return sync_counters(g);
+}
+
+int rsf_gather_valid_classes(rsf_grid_t g, float* rows, int64_t cap_rows, int64_t* n_rows) {
+  if (int rc = check_grid(g)) return rc;
+  if (!g->class_pool) return fail(RSF_ERR_INVALID, "grid was created without rsf_options.num_classes > 2");
+  if (!n_rows) return fail(RSF_ERR_INVALID, "n_rows must not be NULL");
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
+  launch_gather_select(g->view, 0, g->opt.shard_world > 1, S3{0, 0, 0}, S3{0, 0, 0}, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  if (int rc = sync_counters(g)) return rc;
+  const int nblk = g->h_ctr->gather_count;
+  *n_rows = (int64_t)nblk * kBlockVol;
+  if (!rows) return RSF_OK;
+  if (cap_rows < *n_rows) return fail(RSF_ERR_CAPACITY, "need %lld rows, capacity %lld", (long long)*n_rows, (long long)cap_rows);
+  if (nblk == 0) return RSF_OK;
+  const int nc = 4 + g->opt.num_classes;
+  DevBuf<float> d_rows(g->stream);
+  RSF_CUDA(d_rows.alloc((size_t)*n_rows * nc));
+  launch_download_class_rows(g->view, g->opt.voxel_size, nblk, g->opt.num_classes, g->class_pool, d_rows.p, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  RSF_CUDA(cudaMemcpyAsync(rows, d_rows.p, (size_t)*n_rows * nc * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
+  RSF_CUDA(cudaStreamSynchronize(g->stream));
+  return RSF_OK;
 }
 
 // cv::Mat::convertTo(CV_32FC1, alpha) multiplies in float: alpha = float(1. / factor)

@@ -14,6 +14,11 @@ void launch_allocate_u16(const GridView& g, const Frame& f, const uint8_t* rgb, 
                          const uint16_t* lt, float depth_alpha, float prob_alpha, FramePixel* frame, cudaStream_t s);
 void launch_select_visible(const GridView& g, const Frame& f, int sm_count, cudaStream_t s);
 void launch_integrate(const GridView& g, const Frame& f, const FramePixel* frame, int sm_count, cudaStream_t s);
+// K-class semantic extension: per-class log-probability planes, updated with the weights from before integrate
+void launch_class_update(const GridView& g, const Frame& f, const FramePixel* frame, const float* class_prob, int K,
+                         float* class_pool, int sm_count, cudaStream_t s);
+void launch_download_class_rows(const GridView& g, float vs, int nblk, int K, const float* class_pool, float* rows, int sm_count,
+                                cudaStream_t s);
 size_t raycast_ranges_bytes(int W, int H);
 // merge != NULL: hits go to the merge planes (depth bits << 32 | payload, system-scope atomicMin) instead of the images
 void launch_raycast(const GridView& g, const Frame& f, float step_size, unsigned* ranges, uchar4* rgba, uchar4* normal,

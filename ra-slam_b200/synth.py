@@ -331,3 +331,16 @@ def render_torch(scene: Scene, K: CameraIntrinsics, H: int, W: int, cam_T_world:
         q = torch.round(depth.to(f64) * depth_factor).clamp(0, 65535)
         depth = (q.to(torch.float32) * np.float32(1.0 / depth_factor)).to(torch.float32)
     return rgb.contiguous(), depth.contiguous(), ht.contiguous(), lt.contiguous()
+
+
+def class_planes(ht: np.ndarray, rgb: np.ndarray, depth: np.ndarray, num_classes: int = 20, seed: int = 2) -> np.ndarray:
+    """K per-class probability planes for the K-class extension: every image region (touch
+    surface x checker colour x coarse depth band) gets a fixed Dirichlet(alpha = 0.3) class distribution drawn from
+    `seed`; returns float32 [K, H, W] with rows summing to 1 and every entry >= 1e-4."""
+    rng = np.random.default_rng(seed)
+    table = rng.dirichlet(np.full(num_classes, 0.3), size=64).astype(np.float64)
+    table = np.maximum(table, 1e-4)
+    table /= table.sum(axis=1, keepdims=True)
+    region = ((ht > 0.5).astype(np.int64) | ((rgb[..., 0] > 128).astype(np.int64) << 1) |
+              (np.clip((depth * 2.0).astype(np.int64), 0, 15) << 2))
+    return np.ascontiguousarray(table[region].transpose(2, 0, 1).astype(np.float32))

@@ -55,6 +55,9 @@ def load():
     for n in ("ora_gather_valid", "ora_gather_valid_semantic"):
         getattr(lib, n).restype = C.c_int64
         getattr(lib, n).argtypes = [_P, _P]
+    lib.ora_integrate_classes.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]
+    lib.ora_gather_valid_classes.restype = C.c_int64
+    lib.ora_gather_valid_classes.argtypes = [_P, _P]
     lib.ora_gather_valid_mesh.restype = C.c_int64
     lib.ora_gather_valid_mesh.argtypes = [_P, _P, _P, _P, _P]
     lib.ora_gather_voxels.restype = C.c_int64
@@ -132,6 +135,18 @@ class OracleGrid:
     def GatherVoxels(self, volumn):
         b = volumn.as_array()
         return self._rows(self.lib.ora_gather_voxels, 4, b.ctypes.data)
+
+    def IntegrateClasses(self, rgb, depth, class_prob, max_depth, intrinsics, cam_T_world):
+        H, W = depth.shape
+        rgb, depth, class_prob = (np.ascontiguousarray(a) for a in (rgb, depth, class_prob))
+        assert class_prob.dtype == np.float32 and class_prob.shape[1:] == (H, W)
+        self.num_classes = class_prob.shape[0]
+        K, pose = intrinsics.as_array(), cam_T_world.as_array()
+        self.lib.ora_integrate_classes(self.h, rgb.ctypes.data, depth.ctypes.data, class_prob.ctypes.data, self.num_classes, H, W,
+                                       max_depth, K.ctypes.data, pose.ctypes.data)
+
+    def GatherValidClasses(self):
+        return self._rows(self.lib.ora_gather_valid_classes, 4 + self.num_classes)
 
     def GatherValidMesh(self):
         nt = C.c_int64(0)

@@ -435,3 +435,40 @@ def test_integrate_u16_equals_converted_float_path(rsf, synth):
         assert np.array_equal(ex[1].view(np.uint32), ey[1].view(np.uint32))
         assert np.array_equal(ex[2], ey[2])
         assert np.array_equal(ex[3].view(np.uint32), ey[3].view(np.uint32))
+
+
+# ---- K-class semantic fusion (extension) ------------------------------------------------------
+def test_class_fusion_matches_oracle(rsf, synth):
+    """20 per-class probability planes fused with the TSDF update's own weights and decisions: class probabilities within
+    1e-4 of the oracle's per-step normalised recurrence, argmax labels identical away from ties, the geometry / colour /
+    binary channel untouched (bit-identical to the oracle)."""
+    K = 20
+    seq = synth.config3(n_frames=40)
+    seq = synth.Sequence(seq.name, synth.scaled(seq.K, 160 / 640.0, 120 / 480.0), 120, 160, seq.poses, seq.scene, seq.voxel_size,
+                         seq.truncation, seq.max_depth, seq.depth_factor)
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation, num_classes=K, pool_blocks=1 << 15, table_slots_log2=17)
+    o = OracleGrid(seq.voxel_size, seq.truncation, 0)
+    for i in range(16):
+        rgb, depth, ht, lt = seq.frame(i)
+        cls = synth.class_planes(ht, rgb, depth, K)
+        assert abs(float(cls.sum(axis=0).mean()) - 1.0) < 1e-5
+        g.IntegrateClasses(rgb, depth, cls, seq.max_depth, seq.K, seq.poses[i])
+        o.IntegrateClasses(rgb, depth, cls, seq.max_depth, seq.K, seq.poses[i])
+        sg, so = g.stats(), o.stats()
+        for k in ("new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "active_blocks"):
+            assert sg[k] == so[k], (i, k, sg, so)
+    m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
+    parity.assert_block_parity(m)
+    assert m["tsdf_bit_mismatch"] == 0 and m["rgb_mismatch"] == 0
+    a, b = g.GatherValidClasses(), o.GatherValidClasses()
+    assert a.shape == b.shape and a.shape[1] == 4 + K and len(a) > 100_000
+    a, b = a[np.lexsort(a[:, :3].T[::-1])], b[np.lexsort(b[:, :3].T[::-1])]
+    assert np.array_equal(a[:, :4].view(np.uint32), b[:, :4].view(np.uint32))
+    pa, pb = a[:, 4:], b[:, 4:]
+    assert np.abs(pa.sum(axis=1) - 1).max() < 1e-5
+    assert np.abs(pa - pb).max() <= 1e-4, np.abs(pa - pb).max()
+    touched = np.abs(pb - 1.0 / K).max(axis=1) > 1e-6
+    assert touched.mean() > 0.2
+    top2 = np.sort(pb, axis=1)[:, -2:]
+    clear = touched & (top2[:, 1] - top2[:, 0] > 1e-4)
+    assert (pa.argmax(axis=1) == pb.argmax(axis=1))[clear].all()
