@@ -400,12 +400,49 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
         e2e_u16 = {"value": K / (time.perf_counter() - t0), "unit": UNIT, "h2d_bytes_per_step": 9 * H * Wd,
                    "d2h_bytes_per_step": 12 * H * Wd, "api": "rsf_integrate_u16_async + rsf_raycast_async + rsf_wait"}
         grid_u.close()
+    # (d) configs[2]: 20 per-class probability planes fused per frame (rsf_integrate_classes_device) + raycast, frames
+    #     resident in HBM; then the export for evaluation (GatherValidSemantic / GatherValidClasses), timed separately
+    classes20 = None
+    try:
+        synth = importlib.import_module("ra-slam_b200.synth")
+        Kc, Kn, Wn = 20, min(K, 24), min(W, 8)
+        grid_c = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank, stream=stream.cuda_stream, num_classes=Kc)
+        c_frames = []
+        for rgb, depth, ht, lt in frames[:Wn + Kn]:
+            c_frames.append((torch.from_numpy(rgb).to(dev), torch.from_numpy(depth).to(dev),
+                             torch.from_numpy(synth.class_planes(ht, rgb, depth, Kc)).to(dev)))
+        for i in range(Wn):
+            grid_c.IntegrateClasses(*c_frames[i], seq.max_depth, seq.K, seq.poses[i])
+            grid_c.RayCast(rmax, cam, seq.poses[i], out=out)
+        torch.cuda.synchronize()
+        evc = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kn)]
+        for k in range(Kn):
+            flush.zero_()
+            evc[k][0].record()
+            grid_c.IntegrateClasses(*c_frames[Wn + k], seq.max_depth, seq.K, seq.poses[Wn + k])
+            grid_c.RayCast(rmax, cam, seq.poses[Wn + k], out=out)
+            evc[k][1].record()
+        torch.cuda.synchronize()
+        c_ms = sum(a.elapsed_time(b) for a, b in evc)
+        t0 = time.perf_counter()
+        rows = grid_c.GatherValidSemantic()
+        t1 = time.perf_counter()
+        crow = grid_c.GatherValidClasses()
+        t2 = time.perf_counter()
+        classes20 = {"classes": Kc, "steps": Kn, "value": Kn / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms / Kn,
+                     "class_input_bytes_per_step": 4 * Kc * H * Wd,
+                     "export_gather_valid_semantic": {"rows": int(len(rows)), "bytes": int(rows.nbytes), "ms": 1e3 * (t1 - t0)},
+                     "export_gather_valid_classes": {"rows": int(len(crow)), "bytes": int(crow.nbytes), "ms": 1e3 * (t2 - t1)}}
+        grid_c.close()
+        del c_frames
+    except Exception as e:      # the extension must never take the headline measurement down with it
+        classes20 = {"error": repr(e)}
     P = H * Wd
     upd = tot1["updated_voxels"] - tot0["updated_voxels"]
     vis = tot1["visible_blocks"] - tot0["visible_blocks"]
     int_ms, int_n = prof["integrate"]
     alg = 24.0 * upd + 12.0 * vis + 15.0 * P * int_n
-    return {"steps": K, "warmup": W, "unit": UNIT, "value": K / (dev_ms * 1e-3), "ms_per_step": dev_ms / K,
+    return {"classes20": classes20,"steps": K, "warmup": W, "unit": UNIT, "value": K / (dev_ms * 1e-3), "ms_per_step": dev_ms / K,
             "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 15 * P, "d2h_bytes_per_step": 12 * P},
             "e2e_u16_inputs": e2e_u16,
             "kernels_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
