@@ -227,6 +227,21 @@ class TSDFGrid {
     check((asynchronous ? rsf_integrate_u16_async : rsf_integrate_u16)(g_, img_rgb, img_depth, img_ht, img_lt, rows, cols,
                                                                         depth_factor, max_depth, K, pose.data()));
   }
+  // K-class semantic extension (grid created with rsf_options.num_classes = K > 2): class_prob = K planes of
+  // rows*cols float probabilities; rows of 4 + K floats (x, y, z, tsdf, p_0 .. p_{K-1}) on export.
+  void IntegrateClasses(const uint8_t* img_rgb, const float* img_depth, const float* class_prob, int rows, int cols, float max_depth,
+                        const CameraIntrinsics<float>& intrinsics, const SE3<float>& cam_T_world) {
+    const float K[4] = {intrinsics.fx, intrinsics.fy, intrinsics.cx, intrinsics.cy};
+    const auto pose = cam_T_world.as_pose();
+    check(rsf_integrate_classes(g_, img_rgb, img_depth, class_prob, rows, cols, max_depth, K, pose.data()));
+  }
+  std::vector<float> GatherValidClasses(int num_classes) {
+    int64_t n = 0;
+    check(rsf_gather_valid_classes(g_, nullptr, 0, &n));
+    std::vector<float> rows((size_t)n * (4 + num_classes));
+    if (n) check(rsf_gather_valid_classes(g_, rows.data(), n, &n));
+    return rows;
+  }
   void Synchronize() { check(rsf_synchronize(g_)); }
 
   // voxel_tsdf.cu:885-902.  rgba / normal: img_h*img_w*4 bytes each; depth / prob: img_h*img_w floats.

@@ -472,3 +472,31 @@ def test_class_fusion_matches_oracle(rsf, synth):
     top2 = np.sort(pb, axis=1)[:, -2:]
     clear = touched & (top2[:, 1] - top2[:, 0] > 1e-4)
     assert (pa.argmax(axis=1) == pb.argmax(axis=1))[clear].all()
+
+
+def test_new_entry_points_reject_bad_arguments(rsf):
+    """Error behaviour of the entry points added this round: status codes, never a crash."""
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=1024, table_slots_log2=12)
+    K, T = rsf.CameraIntrinsics(100.0, 100.0, 31.5, 23.5), rsf.SE3()
+    rgb = np.zeros((48, 64, 3), np.uint8)
+    d16 = np.full((48, 64), 5000, np.uint16)
+    with pytest.raises(rsf.RsfError) as e:                       # ht without lt
+        g.IntegrateU16(rgb, d16, d16, None, 5000.0, 4.0, K, T)
+    assert e.value.code == rsf.RSF_ERR_INVALID
+    with pytest.raises(rsf.RsfError) as e:                       # depth_factor must be positive
+        g.IntegrateU16(rgb, d16, None, None, 0.0, 4.0, K, T)
+    assert e.value.code == rsf.RSF_ERR_INVALID
+    with pytest.raises(rsf.RsfError) as e:                       # max_depth outside the validated range
+        g.IntegrateU16(rgb, d16, None, None, 5000.0, float("nan"), K, T)
+    assert e.value.code == rsf.RSF_ERR_INVALID
+    g.num_classes = 5                                            # grid was created without class planes
+    with pytest.raises(rsf.RsfError) as e:
+        g.IntegrateClasses(rgb, np.ones((48, 64), np.float32), np.full((5, 48, 64), 0.2, np.float32), 4.0, K, T)
+    assert e.value.code == rsf.RSF_ERR_INVALID
+    with pytest.raises(rsf.RsfError):
+        g.GatherValidClasses()
+    with pytest.raises(rsf.RsfError) as e:
+        rsf.TSDFGrid(0.01, 0.06, pool_blocks=1024, table_slots_log2=12, num_classes=65)
+    assert e.value.code == rsf.RSF_ERR_INVALID
+    g.IntegrateU16(rgb, d16, None, None, 5000.0, 4.0, K, T)       # and the grid is still usable
+    assert g.NumActiveBlock() > 0
