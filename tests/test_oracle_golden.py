@@ -196,3 +196,20 @@ def test_marching_cubes_on_a_sphere():
     assert len(np.unique(tw)) - len(ue) + len(tw) == 2                   # Euler characteristic of a sphere
     area = 0.5 * np.linalg.norm(np.cross(v[t[:, 1]] - v[t[:, 0]], v[t[:, 2]] - v[t[:, 0]]), axis=1).sum()
     assert abs(area / (4 * np.pi * (r * vs) ** 2) - 1) < 0.02
+
+
+def test_class_recurrence_reduces_to_the_binary_fusion(synth):
+    # the K-class form with the two planes (ht, lt) must reproduce the reference's binary update
+    # (voxel_tsdf.cu:241-248) on every voxel: p_0 == probability, p_0 + p_1 == 1
+    seq = synth.config2(n_frames=300, H=72, W=96)
+    a, b = OracleGrid(0.01, 0.06, 0), OracleGrid(0.01, 0.06, 0)
+    for i in range(8):
+        rgb, depth, ht, lt = seq.frame(i)
+        a.Integrate(rgb, depth, ht, lt, seq.max_depth, seq.K, seq.poses[i])
+        b.IntegrateClasses(rgb, depth, np.stack([ht, lt]), seq.max_depth, seq.K, seq.poses[i])
+    ra, rb = a.GatherValidSemantic(), b.GatherValidClasses()
+    assert ra.shape[0] == rb.shape[0] and rb.shape[1] == 6
+    assert np.array_equal(ra[:, :4].view(np.uint32), rb[:, :4].view(np.uint32))      # geometry untouched by the class path
+    assert np.abs(rb[:, 4] + rb[:, 5] - 1).max() < 1e-6
+    assert np.abs(ra[:, 4] - rb[:, 4]).max() < 2e-6
+    assert (np.abs(ra[:, 4] - 0.5) > 0.05).mean() > 0.2                                # and the test is not vacuous
