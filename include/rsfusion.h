@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RSF_ABI_VERSION 1
+#define RSF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RSF_API __attribute__((visibility("default")))
@@ -85,6 +85,10 @@ typedef struct rsf_frame_stats {
   int64_t updated_voxels;  /* voxels that passed sdf > -truncation                          */
   int64_t carved_blocks;   /* blocks removed by space carving                               */
   int64_t high_water;      /* pool slots ever used                                          */
+  int64_t culled_blocks;   /* of visible_blocks: proven un-updatable (occluded) and skipped */
+  int64_t table_keys;      /* claimed hash-table slots = alive blocks + ghosts of carved    */
+                           /* ones; the table is rebuilt when this passes half its size     */
+  int64_t table_rebuilds;  /* rebuilds since creation                                       */
 } rsf_frame_stats;
 
 RSF_API void rsf_default_options(rsf_options* opts);

@@ -46,7 +46,8 @@ class rsf_options(C.Structure):
 
 class rsf_frame_stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
-                ("active_blocks", "new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "high_water")]
+                ("active_blocks", "new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "high_water",
+                 "culled_blocks", "table_keys", "table_rebuilds")]
 
 
 # every symbol include/rsfusion.h declares: name -> (restype, argtypes)
@@ -113,7 +114,7 @@ def load_library(path: str | None = None):
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rsf_abi_version() != 1:
+    if lib.rsf_abi_version() != 2:
         raise RsfError(RSF_ERR_INVALID, "ABI version mismatch")
     if path is None:
         _lib = lib

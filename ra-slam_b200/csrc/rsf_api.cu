@@ -84,11 +84,14 @@ struct rsf_grid_s {
   } out[kSlots];
   unsigned in_next = 0, out_next = 0;
   float4* d_frame = nullptr;       // staged frame records (written by allocate, read by integrate)
+  float* d_tiles = nullptr;        // per-16x16-tile maximum usable depth (occlusion culling in select_visible)
+  int int_ctas_per_sm = 8;         // resident integrate_kernel CTAs per SM on this grid's device
   unsigned* d_ranges = nullptr;   // per-tile depth ranges of the raycast pre-pass
   float* class_pool = nullptr;    // K-class extension: [pool_blocks][K][512] un-normalised log-probabilities
   // pinned mirror of the device counters
   Counters* h_ctr = nullptr;
   rsf_frame_stats last{};
+  int64_t table_rebuilds = 0;
   // optional per-kernel CUDA-event timing (rsf_profile_*)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[RSF_PROF_NUM];
@@ -129,9 +132,12 @@ int sync_counters(rsf_grid_t g) {
   g->last.active_blocks = (int64_t)g->view.pool_blocks - c.free_count;
   g->last.high_water = c.high_water;
   g->last.new_blocks = (int64_t)c.new_blocks;
-  g->last.visible_blocks = c.vis_count;
+  g->last.visible_blocks = (int64_t)c.vis_count + c.culled;   // culled blocks are visible in the reference's sense
   g->last.updated_voxels = (int64_t)c.updated_voxels;
   g->last.carved_blocks = (int64_t)c.carved_blocks;
+  g->last.culled_blocks = c.culled;
+  g->last.table_keys = c.table_keys;
+  g->last.table_rebuilds = g->table_rebuilds;
   if (c.error) {
     const unsigned e = c.error;
     cudaMemsetAsync(&g->view.ctr->error, 0, sizeof(unsigned), g->stream);
@@ -179,7 +185,8 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const vo
   RSF_CUDA(cudaStreamWaitEvent(g->s_side, g->ev_fork, 0));
   {
     ProfScope p(g, RSF_PROF_SELECT, g->s_side);
-    launch_select_visible(g->view, f, g->sm_count, g->s_side);
+    launch_depth_tiles(depth, u16, depth_alpha, f.W, f.H, f.max_depth, g->d_tiles, g->s_side);
+    launch_select_visible(g->view, f, g->d_tiles, g->sm_count, g->s_side);
   }
   RSF_CUDA(cudaEventRecord(g->ev_join, g->s_side));
   {
@@ -198,7 +205,7 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const vo
     launch_class_update(g->view, f, g->d_frame, class_prob, g->opt.num_classes, g->class_pool, g->sm_count, g->stream);
   {
     ProfScope p(g, RSF_PROF_INTEGRATE);
-    launch_integrate(g->view, f, g->d_frame, g->sm_count, g->stream);
+    launch_integrate(g->view, f, g->d_frame, g->sm_count, g->int_ctas_per_sm, g->stream);
   }
   RSF_CUDA(cudaGetLastError());
   return RSF_OK;
@@ -287,6 +294,8 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   if (o.table_slots_log2 > 30 || ((size_t)1 << o.table_slots_log2) < 2 * (size_t)o.pool_blocks)
     return fail(RSF_ERR_INVALID, "table_slots_log2=%d must give >= 2x pool_blocks=%d slots", o.table_slots_log2, o.pool_blocks);
   if (o.shard_rank < 0 || o.shard_rank >= o.shard_world) return fail(RSF_ERR_INVALID, "shard_rank outside [0, shard_world)");
+  // shard_wanted shifts by shard_shift and loops over (2 halo + 1)^3 neighbours: keep both small (int16 block coordinates)
+  if (o.shard_shift > 12 || o.shard_halo > 4) return fail(RSF_ERR_INVALID, "shard_shift must be <= 12 and shard_halo <= 4");
   if (o.flags & ~(unsigned)RSF_FLAG_EXTERNAL_STREAM) return fail(RSF_ERR_INVALID, "unknown bits in flags");
   if (o.num_classes == 2) o.num_classes = 0;
   if (o.num_classes != 0 && (o.num_classes < 3 || o.num_classes > 64)) return fail(RSF_ERR_INVALID, "num_classes must be 0, 2 or 3..64");
@@ -335,6 +344,8 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   A((void**)&v.gather_list, (size_t)o.pool_blocks * sizeof(int));
   A((void**)&v.ctr, sizeof(Counters));
   A((void**)&g->d_frame, P * sizeof(float4));
+  A((void**)&g->d_tiles, (P / 16 + 4096) * sizeof(float));   // ceil(W/16) ceil(H/16) <= P/16 + 1 for any aspect ratio
+  g->int_ctas_per_sm = integrate_ctas_per_sm();
   for (auto& sl : g->in) {
     A((void**)&sl.rgb, P * 3);
     A((void**)&sl.depth, P * sizeof(float));
@@ -382,7 +393,7 @@ int rsf_destroy(rsf_grid_t g) {
   if (g->s_h2d) cudaStreamSynchronize(g->s_h2d);
   if (g->s_d2h) cudaStreamSynchronize(g->s_d2h);
   if (g->s_side) cudaStreamSynchronize(g->s_side);
-  void* ptrs[] = {v.table, v.pool, v.meta, v.heap, v.vis_list, v.gather_list, v.ctr, g->d_frame, g->d_ranges, g->class_pool};
+  void* ptrs[] = {v.table, v.pool, v.meta, v.heap, v.vis_list, v.gather_list, v.ctr, g->d_frame, g->d_tiles, g->d_ranges, g->class_pool};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& sl : g->in) {
@@ -460,8 +471,9 @@ int rsf_integrate_classes_device(rsf_grid_t g, const uint8_t* rgb, const float* 
   Frame f;
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
-  // binary channel: ht = lt = plane 0 -> ln ht - ln lt = 0, the prior is kept
-  return enqueue_integrate(g, f, rgb, depth, class_prob, class_prob, nullptr, false, 1.f, 1.f, class_prob);
+  // binary channel: no ht / lt images -> the staged observation is ln 1 - ln 1 = 0 exactly and the prior is kept
+  // (feeding ht = lt = a class plane would give ln 0 - ln 0 = NaN wherever that plane is 0, e.g. one-hot maps)
+  return enqueue_integrate(g, f, rgb, depth, nullptr, nullptr, nullptr, false, 1.f, 1.f, class_prob);
 }
 
 int rsf_integrate_classes(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* class_prob, int H, int W,

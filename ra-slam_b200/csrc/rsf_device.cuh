@@ -38,6 +38,11 @@ constexpr int kValPending = -2;   // a thread is attaching a block right now
 
 constexpr uint32_t kMetaAlive = 1u;
 constexpr uint32_t kMetaFresh = 2u;   // slab contents not yet materialised (see integrate kernel)
+// Set on blocks whose voxels were written by the table-level hooks (rsf_allocate_blocks / rsf_assign_voxels) and have
+// not been through the integrate kernel's carve test since: such a block may hold min|tsdf| >= 0.9 and must reach the
+// integrate kernel (which carves it, voxel_tsdf.cu:253-276) even when no voxel of it can be updated.  See
+// select_visible_kernel's occlusion culling.
+constexpr uint32_t kMetaNoCull = 4u;
 
 constexpr unsigned kErrPoolFull = 1u;
 constexpr unsigned kErrTableFull = 2u;
@@ -112,9 +117,9 @@ struct Counters {
   int free_count;      // stack pointer into heap[]: heap[0 .. free_count) are free pool slots
   int high_water;      // 1 + largest pool index ever handed out
   unsigned error;      // sticky kErr* bits
-  int pad0;
+  int table_keys;      // table slots whose key is claimed (alive blocks + ghosts of carved ones): the probe-chain load
   int vis_count;       // length of the visible list built by the select kernel
-  int pad1;
+  int culled;          // visible blocks the select kernel proved un-updatable this frame (occluded) and left out
   unsigned long long new_blocks, updated_voxels, carved_blocks;
   int gather_count;    // length of the list built by the gather-select kernel
   int pad2;
@@ -312,7 +317,10 @@ __device__ inline int table_find_or_claim_slot(const GridView& g, uint64_t key, 
     uint64_t k = *(volatile uint64_t*)&g.table[s].key;
     if (k == kEmptyKey) {
       k = atomicCAS((unsigned long long*)&g.table[s].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
-      if (k == kEmptyKey) return (int)s;
+      if (k == kEmptyKey) {
+        atomicAdd(&g.ctr->table_keys, 1);
+        return (int)s;
+      }
     }
     if (k == key) return (int)s;
     s = (s + 1) & g.slot_mask;

@@ -12,8 +12,13 @@ void launch_allocate(const GridView& g, const Frame& f, const uint8_t* rgb, cons
                      const float* lt, FramePixel* frame, cudaStream_t s);
 void launch_allocate_u16(const GridView& g, const Frame& f, const uint8_t* rgb, const uint16_t* depth, const uint16_t* ht,
                          const uint16_t* lt, float depth_alpha, float prob_alpha, FramePixel* frame, cudaStream_t s);
-void launch_select_visible(const GridView& g, const Frame& f, int sm_count, cudaStream_t s);
-void launch_integrate(const GridView& g, const Frame& f, const FramePixel* frame, int sm_count, cudaStream_t s);
+// per-tile maximum of the usable depth (16x16-pixel tiles) for the occlusion culling in select_visible
+void launch_depth_tiles(const void* depth, bool u16, float depth_alpha, int W, int H, float max_depth, float* tiles, cudaStream_t s);
+size_t depth_tiles_count(int W, int H);
+// tiles == NULL: no culling (every alive block with a corner in view is selected)
+void launch_select_visible(const GridView& g, const Frame& f, const float* tiles, int sm_count, cudaStream_t s);
+int integrate_ctas_per_sm();   // resident CTAs per SM of integrate_kernel on the current device
+void launch_integrate(const GridView& g, const Frame& f, const FramePixel* frame, int sm_count, int ctas_per_sm, cudaStream_t s);
 // K-class semantic extension: per-class log-probability planes, updated with the weights from before integrate
 void launch_class_update(const GridView& g, const Frame& f, const FramePixel* frame, const float* class_prob, int K,
                          float* class_pool, int sm_count, cudaStream_t s);

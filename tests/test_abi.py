@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(rsf):
     out = subprocess.check_output(["nm", "-D", "--defined-only", rsf.LIB_PATH], text=True)
     exported = set(re.findall(r"\bT (rsf_\w+)", out))
     assert exported == set(declared), exported ^ set(declared)
-    assert lib.rsf_abi_version() == 1
+    assert lib.rsf_abi_version() == 2
 
 
 def test_library_is_sm100a_native(rsf):
