@@ -39,7 +39,12 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("RSF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+# NCCL's own log: leave whatever the caller set; otherwise INFO / INIT (the communicator's "nranks" lines) to stderr, so
+# stdout stays the one JSON line
+if "NCCL_DEBUG" not in os.environ:
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "frames/s integrate+raycast 640x480 semantic (TUM fr1-shaped)"
 METRICS = {"tum": METRIC, "scannet": "frames/s integrate+raycast 640x480 semantic (ScanNet-shaped)",
@@ -59,6 +64,9 @@ def parse_args():
     ap.add_argument("--workload", choices=["tum", "scannet", "scannet-hires", "l515"], default="tum",
                     help="tum = BASELINE.json configs[1] (the headline line); the others are configs[2] / configs[3] shapes")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short 1296x968 ScanNet-shaped measurement")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the spatially sharded configs[4] measurement")
+    ap.add_argument("--sharded-height", type=int, default=968)
+    ap.add_argument("--sharded-width", type=int, default=1296)
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -597,6 +605,16 @@ def run_native(args):
         t = torch.tensor([dev_ms, warm_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, warm_ms, e2e_s = (float(x) for x in t.tolist())
+    # ---------------- configs[4]: one large scene spatially sharded over the N GPUs (strong scaling) ----------------
+    # every rank takes part; rank 0 gets the result.  N = 1 is the unsharded baseline of the same frames.
+    sharded = None
+    if not args.no_sharded:
+        import bench_sharded
+        try:
+            sharded = bench_sharded.run(rank, local_rank, world, steps=min(max(K, 8), 24), warmup=12, H=args.sharded_height,
+                                        W=args.sharded_width)
+        except Exception as e:      # never take the headline line down
+            sharded = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -643,6 +661,7 @@ def run_native(args):
         "clocks": clocks,
         "map": {"active_blocks": stats_end["active_blocks"], "high_water": stats_end["high_water"]},
     }
+    line["sharded_config5"] = sharded
     if world == 1 and args.workload == "tum" and not args.no_secondary:
         synth = importlib.import_module("ra-slam_b200.synth")
         s2 = synth.config3(n_frames=200, hires=True)

@@ -183,6 +183,38 @@ RSF_API int rsf_raycast_merge_device(rsf_grid_t g, float max_depth, int H, int W
 RSF_API int rsf_merge_finalize_device(rsf_grid_t g, int H, int W, uint64_t* merge_planes, int n_planes, uint8_t* rgba,
                                       uint8_t* normal, float* depth, float* prob);
 
+/* One frame of a spatially sharded scene in ONE call per rank (new): integrate the frame into this rank's shard, raycast
+ * the virtual view against it with the min-depth merge fused in, raise this rank's arrival flag in the presenting rank's
+ * memory and -- on the presenting rank -- wait for all flags, unpack the merged planes into the images and re-arm them.
+ * Everything is enqueued on the grid's stream; nothing blocks the host and no host-side barrier is involved.
+ *
+ * rsf_shard_link describes the presenting rank's buffers as seen from THIS process (its own device memory on the
+ * presenting rank, NVLink peer mappings elsewhere -- torch symmetric memory, cudaIpc, ...):
+ *   planes[2]  two sets (frame parity) of n_planes * H * W 64-bit words preset to all-ones; a set is re-armed by the
+ *              presenting rank when it unpacks it, and written again two frames later -- the caller must order frame
+ *              k + 2's input on every rank after frame k's call on the presenting rank (a broadcast of the frame from
+ *              the presenting rank on the same stream does that);
+ *   flags      shard_world 32-bit words preset to 0; rank r stores the frame sequence number into flags[r] (system-scope
+ *              release), the presenting rank acquires them.  All ranks must issue the same sequence of calls.
+ * With shard_world == 1 no link is needed and the call is rsf_integrate_device + rsf_raycast_device.
+ * Inputs are device pointers (the frame as rsf_integrate_device takes it); the outputs are device pointers used on the
+ * presenting rank only (any may be NULL). */
+typedef struct rsf_shard_link {
+  uint64_t* planes[2];
+  uint32_t* flags;
+  int n_planes;            /* 1..3 planes per set: rgba | + normal | + prob                   */
+  unsigned skip_mask;      /* bit k set: nobody wants plane k (1 = normal, 2 = prob); it is   */
+                           /* neither written nor unpacked.  Must be the same on all ranks.  */
+  int root;                /* presenting rank                                                 */
+  int H, W;                /* image size the planes hold                                      */
+} rsf_shard_link;
+RSF_API int rsf_shard_set_link(rsf_grid_t g, const rsf_shard_link* link);
+RSF_API int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
+                                   int H, int W, float max_depth, const float K[4], const float pose[7],
+                                   float raycast_max_depth, int rc_H, int rc_W, const float rc_K[4],
+                                   const float rc_pose[7], uint8_t* rgba, uint8_t* normal, float* depth_out,
+                                   float* prob_out);
+
 /* Block until everything enqueued on the grid's stream is done; surfaces device-side errors
  * (pool/table exhaustion) of the asynchronous variants. */
 RSF_API int rsf_synchronize(rsf_grid_t g);

@@ -44,6 +44,11 @@ class rsf_options(C.Structure):
     ]
 
 
+class rsf_shard_link(C.Structure):
+    _fields_ = [("planes", C.c_void_p * 2), ("flags", C.c_void_p), ("n_planes", C.c_int), ("skip_mask", C.c_uint), ("root", C.c_int),
+                ("H", C.c_int), ("W", C.c_int)]
+
+
 class rsf_frame_stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("active_blocks", "new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "high_water",
@@ -74,6 +79,9 @@ ABI = {
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_merge_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, C.c_int]),
     "rsf_merge_finalize_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
+    "rsf_shard_set_link": (C.c_int, [_P, C.POINTER(rsf_shard_link)]),
+    "rsf_shard_frame_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4,
+                                         C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_synchronize": (C.c_int, [_P]),
     "rsf_num_active_blocks": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rsf_get_stats": (C.c_int, [_P, C.POINTER(rsf_frame_stats)]),
@@ -257,6 +265,7 @@ class TSDFGrid:
         o.shard_rank, o.shard_world, o.shard_shift, o.shard_halo = shard_rank, shard_world, shard_shift, shard_halo
         o.num_classes = num_classes
         self.num_classes = num_classes
+        self.stream_handle = stream          # None: library-owned stream (not torch's current stream)
         if stream is not None:
             o.stream = stream or None
             o.flags = 1          # RSF_FLAG_EXTERNAL_STREAM: use it even if it is the default stream (0)
@@ -355,6 +364,28 @@ class TSDFGrid:
         ptr = {k: (out[k].data_ptr() if k in out else None) for k in ("rgba", "normal", "depth", "prob")}
         _check(self._lib.rsf_merge_finalize_device(self._h, H, W, merge_ptr, n_planes, ptr["rgba"], ptr["normal"],
                                                    ptr["depth"], ptr["prob"]))
+        return out
+
+    def ShardSetLink(self, planes0: int, planes1: int, flags: int, n_planes: int, root: int, H: int, W: int, skip_mask: int = 0):
+        """rsf_shard_set_link: device addresses (in THIS process) of the presenting rank's merge planes / arrival flags."""
+        ln = rsf_shard_link()
+        ln.planes[0], ln.planes[1], ln.flags = planes0, planes1, flags
+        ln.n_planes, ln.root, ln.H, ln.W, ln.skip_mask = n_planes, root, H, W, skip_mask
+        _check(self._lib.rsf_shard_set_link(self._h, C.byref(ln)))
+
+    def ShardFrame(self, img_rgb, img_depth, img_ht, img_lt, max_depth: float, intrinsics: CameraIntrinsics, cam_T_world: SE3,
+                   raycast_max_depth: float, virtual_cam: CameraParams, rc_cam_T_world: SE3, out: dict | None = None):
+        """rsf_shard_frame_device: integrate + raycast-merge + arrival flag (+ unpack on the presenting rank) in one
+        call; torch CUDA tensors in, `out` (torch CUDA tensors, presenting rank only) filled asynchronously."""
+        H, W = img_depth.shape
+        K, pose = intrinsics.as_array(), cam_T_world.as_array()
+        rK, rpose = virtual_cam.intrinsics.as_array(), rc_cam_T_world.as_array()
+        out = out or {}
+        ptr = {k: (out[k].data_ptr() if k in out else None) for k in ("rgba", "normal", "depth", "prob")}
+        _check(self._lib.rsf_shard_frame_device(self._h, img_rgb.data_ptr(), img_depth.data_ptr(), img_ht.data_ptr(),
+                                                img_lt.data_ptr(), H, W, max_depth, _fptr(K), _fptr(pose), raycast_max_depth,
+                                                virtual_cam.img_h, virtual_cam.img_w, _fptr(rK), _fptr(rpose),
+                                                ptr["rgba"], ptr["normal"], ptr["depth"], ptr["prob"]))
         return out
 
     def synchronize(self):
@@ -477,6 +508,15 @@ class TSDFGrid:
             order = np.argsort(block_keys(coords), kind="stable")
             coords, tsdf, rgbw, prob = coords[order], tsdf[order], rgbw[order], prob[order]
         return coords, tsdf, rgbw, prob
+
+    def ExportBlockCoords(self, owned_only: bool = False) -> np.ndarray:
+        """n x 3 i16 block coordinates of the alive blocks (no voxel data)."""
+        n = C.c_int64(0)
+        _check(self._lib.rsf_export_blocks(self._h, int(owned_only), None, None, None, None, 0, C.byref(n)))
+        coords = np.empty((n.value, 3), np.int16)
+        if n.value:
+            _check(self._lib.rsf_export_blocks(self._h, int(owned_only), coords.ctypes.data, None, None, None, n.value, C.byref(n)))
+        return coords
 
     # -- table / pool level hooks (utils/tests/voxel_hash_test.cu) -------------------------------
     def AllocateBlocks(self, block_coords):

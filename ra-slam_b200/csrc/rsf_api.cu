@@ -92,6 +92,10 @@ struct rsf_grid_s {
   Counters* h_ctr = nullptr;
   rsf_frame_stats last{};
   int64_t table_rebuilds = 0;
+  // sharded frame (rsf_shard_frame_device): the presenting rank's planes / flags as mapped into this process
+  rsf_shard_link link{};
+  bool linked = false;
+  unsigned shard_seq = 0;
   // optional per-kernel CUDA-event timing (rsf_profile_*)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[RSF_PROF_NUM];
@@ -606,6 +610,65 @@ int rsf_merge_finalize_device(rsf_grid_t g, int H, int W, uint64_t* merge_planes
   DeviceGuard dg(g->device);
   launch_merge_finalize(reinterpret_cast<unsigned long long*>(merge_planes), n_planes, H * W, reinterpret_cast<uchar4*>(rgba),
                         reinterpret_cast<uchar4*>(normal), depth, prob, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+int rsf_shard_set_link(rsf_grid_t g, const rsf_shard_link* link) {
+  if (int rc = check_grid(g)) return rc;
+  if (!link) {
+    g->linked = false;
+    return RSF_OK;
+  }
+  if (!link->planes[0] || !link->planes[1] || !link->flags) return fail(RSF_ERR_INVALID, "planes / flags must not be NULL");
+  if (link->n_planes < 1 || link->n_planes > 3) return fail(RSF_ERR_INVALID, "1 <= n_planes <= 3");
+  if (link->root < 0 || link->root >= g->opt.shard_world) return fail(RSF_ERR_INVALID, "root outside [0, shard_world)");
+  if (g->opt.shard_world > 32) return fail(RSF_ERR_INVALID, "rsf_shard_frame_device supports shard_world <= 32");
+  if (link->H <= 0 || link->W <= 0) return fail(RSF_ERR_INVALID, "H, W must be > 0");
+  if (link->skip_mask & ~6u) return fail(RSF_ERR_INVALID, "skip_mask may only name planes 1 and 2");
+  g->link = *link;
+  g->linked = true;
+  g->shard_seq = 0;
+  return RSF_OK;
+}
+
+int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt, int H, int W,
+                           float max_depth, const float K[4], const float pose[7], float raycast_max_depth, int rc_H, int rc_W,
+                           const float rc_K[4], const float rc_pose[7], uint8_t* rgba, uint8_t* normal, float* depth_out,
+                           float* prob_out) {
+  if (int rc = check_grid(g)) return rc;
+  if (!rgb || !depth || !ht || !lt) return fail(RSF_ERR_INVALID, "rgb / depth / ht / lt must not be NULL");
+  Frame f, rf;
+  if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
+  if (int rc = make_frame(g, rc_H, rc_W, raycast_max_depth, rc_K, rc_pose, &rf)) return rc;
+  const int world = g->opt.shard_world, rank = g->opt.shard_rank;
+  if (world > 1) {
+    if (!g->linked) return fail(RSF_ERR_INVALID, "rsf_shard_set_link has not been called");
+    if (rc_H != g->link.H || rc_W != g->link.W) return fail(RSF_ERR_INVALID, "raycast size differs from the linked planes");
+  }
+  DeviceGuard dg(g->device);
+  if (int rc = enqueue_integrate(g, f, rgb, depth, ht, lt)) return rc;
+  if (world <= 1) {
+    ProfScope p(g, RSF_PROF_RAYCAST);
+    launch_raycast(g->view, rf, g->opt.truncation / 2, g->d_ranges, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
+                   depth_out, prob_out, g->sm_count, g->stream);
+    RSF_CUDA(cudaGetLastError());
+    return RSF_OK;
+  }
+  const unsigned seq = ++g->shard_seq;
+  unsigned long long* planes = reinterpret_cast<unsigned long long*>(g->link.planes[seq & 1u]);
+  const int plane_spec = g->link.n_planes | (int)(g->link.skip_mask << 8);
+  {
+    ProfScope p(g, RSF_PROF_RAYCAST);
+    launch_raycast(g->view, rf, g->opt.truncation / 2, g->d_ranges, nullptr, nullptr, nullptr, nullptr, g->sm_count, g->stream,
+                   planes, plane_spec);
+  }
+  launch_shard_signal(g->link.flags + rank, seq, g->stream);
+  if (rank == g->link.root) {
+    launch_shard_wait(g->link.flags, world, seq, g->stream);
+    launch_merge_finalize(planes, plane_spec, rc_H * rc_W, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
+                          depth_out, prob_out, g->sm_count, g->stream);
+  }
   RSF_CUDA(cudaGetLastError());
   return RSF_OK;
 }

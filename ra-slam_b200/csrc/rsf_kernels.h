@@ -31,6 +31,9 @@ void launch_raycast(const GridView& g, const Frame& f, float step_size, unsigned
                     int merge_planes = 0);
 void launch_merge_finalize(unsigned long long* merge, int merge_planes, int P, uchar4* rgba, uchar4* normal, float* depth,
                            float* prob, int sm_count, cudaStream_t s);
+// sharded frame: arrival flags in the presenting rank's memory (system-scope release / acquire)
+void launch_shard_signal(unsigned* flag, unsigned seq, cudaStream_t s);
+void launch_shard_wait(const unsigned* flags, int world, unsigned seq, cudaStream_t s);
 void launch_gather_select(const GridView& g, int mode, int owned_only, S3 lo, S3 hi, int sm_count, cudaStream_t s);
 void launch_download_rows(const GridView& g, float vs, int nblk, int ncol, float* rows, int sm_count, cudaStream_t s);
 void launch_export_blocks(const GridView& g, int nblk, short* coords, float* tsdf, uint32_t* rgbw, float* prob,

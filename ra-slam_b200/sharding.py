@@ -150,6 +150,10 @@ class FusedMinDepthMerge:
         rearm_barrier=False skips the second barrier; only safe when something else orders the root's re-arming of
         the planes before any rank's next raycast -- e.g. the per-frame broadcast from the same root on the same
         stream, as in the integrate -> raycast loop of bench_sharded.py."""
+        # the barrier below runs on torch's current stream: it only orders the raycast kernels if the grid runs there too
+        gs = getattr(grid, "stream_handle", None)
+        assert gs is not None and gs == torch.cuda.current_stream(self.planes.device).cuda_stream, \
+            "FusedMinDepthMerge needs a grid created with stream=torch.cuda.current_stream().cuda_stream"
         grid.RayCastMerge(max_depth, cam, pose, self.root_ptr, self.n_planes)
         self.hdl.barrier()                                      # every rank's atomics have landed
         res = None
@@ -158,6 +162,92 @@ class FusedMinDepthMerge:
         if rearm_barrier:
             self.hdl.barrier()                                  # planes are re-armed before anyone writes again
         return res
+
+
+class ShardedScene:
+    """One large scene spatially sharded over the GPUs of a box, driven with ONE C-ABI call per frame per rank.
+
+    Per frame: the ingest rank's packed frame is broadcast with one NCCL collective (``feed``, on a side stream, so the
+    transfer of frame k + 1 overlaps the kernels of frame k), then every rank calls ``rsf_shard_frame_device`` (``step``,
+    C++): allocate (ownership first) | select -> integrate -> tile ranges -> raycast with the min-depth merge fused in
+    (system-scope atomicMin into the presenting rank's planes over NVLink peer memory) -> arrival flag (release, system
+    scope) in the presenting rank's memory; the presenting rank's stream then waits for all flags on the device and
+    unpacks the planes.  No host-side barrier, no Python between the kernels.
+    Receive buffers and merge planes are double-buffered by frame parity: ``feed`` of frame k + 2 waits (stream event) for
+    ``step`` of frame k on the same rank, which on the presenting rank includes the re-arming of that frame's planes --
+    so nobody can write a plane set before it has been re-armed (rsfusion.h, rsf_shard_link).
+    """
+
+    def __init__(self, voxel_size: float, truncation: float, H: int, W: int, device, *, root: int = 0, outputs=("rgba", "depth", "prob"),
+                 group=None, pool_blocks: int = 0, table_slots_log2: int = 0, shard_shift: int = 4, shard_halo: int = 1):
+        from . import TSDFGrid
+        self.H, self.W, self.root = H, W, root
+        n_planes = 3
+        self.dist_on = dist.is_available() and dist.is_initialized()
+        self.group = group if group is not None else (dist.group.WORLD if self.dist_on else None)
+        self.rank = dist.get_rank(self.group) if self.dist_on else 0
+        self.world = dist.get_world_size(self.group) if self.dist_on else 1
+        self.device = torch.device(device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.grid = TSDFGrid(voxel_size, truncation, device=self.device.index, pool_blocks=pool_blocks,
+                             table_slots_log2=table_slots_log2, shard_rank=self.rank, shard_world=self.world,
+                             shard_shift=shard_shift, shard_halo=shard_halo, stream=self.stream.cuda_stream)
+        self.rx = [torch.empty(frame_nbytes(H, W), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.fed = [None, None]
+        self.side = torch.cuda.Stream(self.device)
+        self.ev_feed = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.n_fed = self.n_stepped = 0
+        self.sym = None
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            P = H * W
+            words = 2 * n_planes * P + 64                    # two plane sets + the arrival flags (32-bit words inside)
+            self.sym = symm_mem.empty(words, dtype=torch.int64, device=self.device)
+            self.sym.fill_(-1)
+            self.sym[2 * n_planes * P:].zero_()
+            self.hdl = symm_mem.rendezvous(self.sym, self.group)
+            base = int(self.hdl.buffer_ptrs[root])
+            skip = (0 if "normal" in outputs else 2) | (0 if "prob" in outputs else 4)
+            self.grid.ShardSetLink(base, base + 8 * n_planes * P, base + 16 * n_planes * P, n_planes, root, H, W, skip)
+            torch.cuda.synchronize(self.device)
+            self.hdl.barrier()                               # everyone's planes are armed before the first frame
+
+    def feed(self, packed_frame=None):
+        """All ranks.  Start moving the next frame: `packed_frame` is the uint8 tensor in `pack_frame` layout on the ingest
+        rank (None elsewhere).  Returns at once; the broadcast runs on a side stream."""
+        j = self.n_fed & 1
+        if self.rank == self.root:
+            assert packed_frame is not None and packed_frame.numel() == self.rx[j].numel()
+        with torch.cuda.stream(self.side):
+            if self.n_fed >= 2:
+                self.side.wait_event(self.ev_done[j])        # frame n_fed - 2 is through: buffer j and plane set j are free
+            else:
+                self.side.wait_stream(self.stream)
+            src = packed_frame if self.rank == self.root else self.rx[j]
+            if self.world > 1:
+                dist.broadcast(src, src=self.root, group=self.group, async_op=True).wait()
+            self.fed[j] = src
+            self.ev_feed[j].record(self.side)
+        self.n_fed += 1
+
+    def step(self, max_depth, intrinsics, cam_T_world, raycast_max_depth, virtual_cam, rc_cam_T_world, out: dict | None = None):
+        """All ranks.  Fuse the oldest fed frame and render the virtual view; `out` (torch CUDA tensors) is filled on the
+        presenting rank, asynchronously on the stream the scene was created on.  Returns `out` there, None elsewhere."""
+        assert self.n_stepped < self.n_fed, "step() without a fed frame"
+        assert torch.cuda.current_stream(self.device).cuda_stream == self.stream.cuda_stream, \
+            "ShardedScene must be stepped on the stream it was created on"
+        j = self.n_stepped & 1
+        self.stream.wait_event(self.ev_feed[j])
+        fr = unpack_frame(self.fed[j], self.H, self.W)
+        self.grid.ShardFrame(*fr, max_depth, intrinsics, cam_T_world, raycast_max_depth, virtual_cam, rc_cam_T_world,
+                             out if self.rank == self.root else None)
+        self.ev_done[j].record(self.stream)
+        self.n_stepped += 1
+        return out if self.rank == self.root else None
+
+    def close(self):
+        self.grid.close()
 
 
 def gather_rows(rows: np.ndarray, group=None) -> np.ndarray:
