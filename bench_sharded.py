@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "configs[4] multi-room building 16x12 m, voxel 0.005, trunc 0.03, max_depth 8, {W}x{H}, dense walk (0.1 m / frame)"
 
 
-def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, shift=4, verify=True, breakdown=True):
+def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, shift=4, verify=True, breakdown=True, flush_l2=True, transport="p2p"):
     """All ranks call this (torch.distributed initialised when world > 1).  Returns the result dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
@@ -44,7 +44,7 @@ def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, sh
     rmax = seq.max_depth * 1.25
     cam = rsf.CameraParams(seq.K, H, W)
     scene = shard.ShardedScene(seq.voxel_size, seq.truncation, H, W, dev, pool_blocks=1 << pool_log2,
-                               table_slots_log2=pool_log2 + 2, shard_shift=shift)
+                               table_slots_log2=pool_log2 + 2, shard_shift=shift, transport=transport)
     grid = scene.grid
     # the ingest rank holds the frames in the wire format (one packed buffer per frame)
     packed = None
@@ -75,13 +75,21 @@ def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, sh
     tot0 = grid.totals()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    scene.stall_events = []
+    import time as _time
+    t_host0 = _time.perf_counter()
     for k in range(K):
-        flush.zero_()
+        if flush_l2:
+            flush.zero_()
         ev[k][0].record()
         step(Wm + k)
         ev[k][1].record()
+    host_us = 1e6 * (_time.perf_counter() - t_host0) / K       # host time to ENQUEUE a step (no synchronisation inside the loop)
     barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
+    # of each step: how long the stream sat waiting for the frame's broadcast to land (0 when the overlap works)
+    stall_ms = sum(ev[k][0].elapsed_time(scene.stall_events[k]) for k in range(K)) / K if len(scene.stall_events) == K else 0.0
+    scene.stall_events = None
     tot1 = grid.totals()
     st = grid.stats()
     merged_depth = out["depth"].clone() if rank == 0 else None
@@ -93,7 +101,7 @@ def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, sh
         Kd = min(K, 8)
         grid.profile_enable(True)
         bev = []
-        scratch = torch.empty_like(scene.rx[0])
+        scratch = torch.empty(scene.nbytes, dtype=torch.uint8, device=dev)
         for k in range(Kd):
             i = Wm + K - Kd + k
             flush.zero_()
@@ -113,8 +121,8 @@ def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, sh
     vals = torch.tensor([ms, float(tot1["updated_voxels"] - tot0["updated_voxels"]), float(st["active_blocks"]),
                          float(tot1["visible_blocks"] - tot0["visible_blocks"])], dtype=torch.float64, device=dev)
     mx, sm = vals.clone(), vals.clone()
-    mine = torch.tensor([(prof[k][0] / prof[k][1] if prof and prof[k][1] else 0.0) for k in ("allocate", "select", "integrate", "raycast")]
-                        + [bc_ms], dtype=torch.float64, device=dev)
+    mine = torch.tensor([(prof[k][0] / prof[k][1] if prof and prof[k][1] else 0.0) for k in ("allocate", "select", "integrate", "raycast", "merge")]
+                        + [bc_ms, stall_ms, ms / K, host_us * 1e-3], dtype=torch.float64, device=dev)
     per_rank = [mine]
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -155,15 +163,19 @@ def run(rank, local, world, steps=24, warmup=12, H=968, W=1296, pool_log2=21, sh
     if rank != 0:
         return None
     ms_max = float(mx[0])
-    names = ("allocate_us", "select_us", "integrate_us", "raycast_us", "broadcast_us")
+    names = ("allocate_us", "select_us", "integrate_us", "raycast_us", "merge_wait_unpack_us", "broadcast_serial_us",
+             "timed_step_stall_on_broadcast_us", "timed_step_us", "host_enqueue_us_per_step")
     return {"metric": "frames/s integrate+raycast, one scene spatially sharded over N GPUs (strong scaling)",
             "value": K / (ms_max * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
             "scaling": "strong", "workload": WORKLOAD.format(W=W, H=H),
             "config": {"shard_shift": shift, "halo_blocks": 1, "pool_blocks": 1 << pool_log2, "raycast_max_depth": rmax,
-                       "l2": "flushed: 256 MiB memset between steps, outside the timed events",
-                       "per_step": ("1 ncclBroadcast of the packed frame (%d bytes, on a side stream: frame k+1 moves while frame k is fused) + "
-                                    "1 rsf_shard_frame_device per rank; merge = system-scope atomicMin into rank 0's planes over NVLink peer "
-                                    "memory, arrival flags instead of a barrier" % shard.frame_nbytes(H, W))
+                       "l2": "flushed: 256 MiB memset between steps, outside the timed events" if flush_l2 else "not flushed",
+                       "frame_transport": transport if world > 1 else None,
+                       "per_step": (("rank 0's copy engines push the packed frame (%d bytes) + a sequence word into every rank's receive buffer over NVLink "
+                                     "(frame k+1 moves while frame k is fused; ranks wait with a stream memory op)" if transport == "p2p" else
+                                     "1 ncclBroadcast of the packed frame (%d bytes) on a side stream") % shard.frame_nbytes(H, W)) +
+                                    " + 1 rsf_shard_frame_device per rank; merge = system-scope atomicMin into rank 0's planes over NVLink peer "
+                                    "memory, arrival flags instead of a barrier"
                        if world > 1 else "1 rsf_shard_frame_device (unsharded grid: integrate + raycast)"},
             "nccl": {"backend": "nccl", "world_size": world, "collectives_per_step": 1 if world > 1 else 0} if world > 1 else None,
             "voxel_updates_per_s_all_ranks": float(sm[1]) / (ms_max * 1e-3),
@@ -184,6 +196,8 @@ def main():
     ap.add_argument("--pool-log2", type=int, default=21)
     ap.add_argument("--shift", type=int, default=4)
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--transport", choices=["p2p", "nccl"], default="p2p")
     ap.add_argument("--gpus", type=int, default=0)
     args = ap.parse_args()
     if "NCCL_DEBUG" not in os.environ:
@@ -194,7 +208,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    res = run(rank, local, world, args.steps, args.warmup, args.height, args.width, args.pool_log2, args.shift, not args.no_verify)
+    res = run(rank, local, world, args.steps, args.warmup, args.height, args.width, args.pool_log2, args.shift, not args.no_verify,
+              flush_l2=not args.no_flush, transport=args.transport)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:

@@ -207,6 +207,13 @@ typedef struct rsf_shard_link {
                            /* neither written nor unpacked.  Must be the same on all ranks.  */
   int root;                /* presenting rank                                                 */
   int H, W;                /* image size the planes hold                                      */
+  /* ---- optional frame transport (rsf_shard_feed_device / rsf_shard_step_device); all zero = the caller moves frames ---- */
+  int frame_H, frame_W;    /* input frame size; a packed frame is [rgb u8 x3 | depth f32 | ht f32 | lt f32] = 15 H W bytes  */
+  uint8_t* rx[2];          /* this rank's receive buffers (frame parity), device memory its tree parent can write    */
+  uint32_t* frame_flag;    /* 2 words next to them, preset 0: frame_flag[j] = sequence number of the frame in rx[j]  */
+  int n_kids;              /* children of this rank in the push tree rooted at `root` (0..2)                         */
+  uint8_t* kid_rx[2][2];   /* [kid][parity]: the children's receive buffers, peer-mapped into this process           */
+  uint32_t* kid_flag[2];   /* [kid]: the children's frame_flag words, peer-mapped                                    */
 } rsf_shard_link;
 RSF_API int rsf_shard_set_link(rsf_grid_t g, const rsf_shard_link* link);
 RSF_API int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float* depth, const float* ht, const float* lt,
@@ -214,6 +221,29 @@ RSF_API int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float
                                    float raycast_max_depth, int rc_H, int rc_W, const float rc_K[4],
                                    const float rc_pose[7], uint8_t* rgba, uint8_t* normal, float* depth_out,
                                    float* prob_out);
+/* The same frame with the transport inside the library: two calls per frame per rank, nothing else on the host.
+ * rsf_shard_feed_device starts moving the NEXT frame down a binary tree of copy-engine pushes rooted at the presenting /
+ * ingest rank (packed_frame: device pointer on that rank, ignored elsewhere): each rank's copy engines write the frame
+ * into its children's receive buffers over NVLink and then the frame's sequence number into their frame_flag word
+ * (stream memory operation); a rank forwards as soon as its own copy has landed (stream wait on its flag).  No SM and no
+ * collective kernel is involved, so the transfer of frame k + 1 overlaps the kernels of frame k.  The ingest rank gates
+ * the push of frame k + 2 on the completion of its own step k, which includes the arrival flags of every rank for frame k,
+ * so a receive buffer is never overwritten before its frame has been consumed.  The packed frame must stay valid on the
+ * ingest rank until the step that consumes it has completed.
+ * rsf_shard_step_device consumes the oldest fed frame: wait (on the device) for its arrival, then exactly
+ * rsf_shard_frame_device on the buffer.  Call order on every rank: feed(0); then per frame k: step(k); feed(k + 1). */
+RSF_API int rsf_shard_feed_device(rsf_grid_t g, const uint8_t* packed_frame);
+RSF_API int rsf_shard_step_device(rsf_grid_t g, float max_depth, const float K[4], const float pose[7], float raycast_max_depth,
+                                  const float rc_K[4], const float rc_pose[7], uint8_t* rgba, uint8_t* normal,
+                                  float* depth_out, float* prob_out);
+
+/* Make the grid's stream wait until the 32-bit word at `flag` (device memory of this GPU, e.g. written by a peer's copy
+ * engine over NVLink) satisfies (int32)(*flag - value) >= 0.  Uses the driver's stream memory operation (no SM involved);
+ * falls back to a one-thread polling kernel.  Used by the sharded scene to order a frame's kernels after the frame's
+ * arrival without a host round trip. */
+RSF_API int rsf_stream_wait_flag_device(rsf_grid_t g, const uint32_t* flag, uint32_t value);
+/* Same on an arbitrary stream of device `device` (cudaStream_t passed as void*): the forwarding streams of the frame tree. */
+RSF_API int rsf_stream_wait_flag_on(int device, void* stream, const uint32_t* flag, uint32_t value);
 
 /* Block until everything enqueued on the grid's stream is done; surfaces device-side errors
  * (pool/table exhaustion) of the asynchronous variants. */
@@ -275,7 +305,8 @@ RSF_API int rsf_retrieve_tsdf_trilinear(rsf_grid_t g, const float* points, int n
  * rsf_profile_enable(g, 1) brackets every subsequent kernel launch with a CUDA event pair on the
  * grid's stream; rsf_profile_read synchronises and returns, per kernel, the summed duration [ms]
  * and launch count since the last read / enable. */
-enum rsf_prof_kernel { RSF_PROF_ALLOCATE = 0, RSF_PROF_SELECT = 1, RSF_PROF_INTEGRATE = 2, RSF_PROF_RAYCAST = 3, RSF_PROF_NUM = 4 };
+enum rsf_prof_kernel { RSF_PROF_ALLOCATE = 0, RSF_PROF_SELECT = 1, RSF_PROF_INTEGRATE = 2, RSF_PROF_RAYCAST = 3,
+                       RSF_PROF_MERGE = 4 /* sharded frame, presenting rank: wait for all arrival flags + unpack */, RSF_PROF_NUM = 5 };
 RSF_API int rsf_profile_enable(rsf_grid_t g, int on);
 RSF_API int rsf_profile_read(rsf_grid_t g, double ms[RSF_PROF_NUM], int64_t launches[RSF_PROF_NUM]);
 /* Running totals since creation: {frames, new_blocks, visible_blocks, updated_voxels, carved_blocks}. */

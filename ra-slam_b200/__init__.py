@@ -46,7 +46,8 @@ class rsf_options(C.Structure):
 
 class rsf_shard_link(C.Structure):
     _fields_ = [("planes", C.c_void_p * 2), ("flags", C.c_void_p), ("n_planes", C.c_int), ("skip_mask", C.c_uint), ("root", C.c_int),
-                ("H", C.c_int), ("W", C.c_int)]
+                ("H", C.c_int), ("W", C.c_int), ("frame_H", C.c_int), ("frame_W", C.c_int), ("rx", C.c_void_p * 2),
+                ("frame_flag", C.c_void_p), ("n_kids", C.c_int), ("kid_rx", (C.c_void_p * 2) * 2), ("kid_flag", C.c_void_p * 2)]
 
 
 class rsf_frame_stats(C.Structure):
@@ -82,6 +83,10 @@ ABI = {
     "rsf_shard_set_link": (C.c_int, [_P, C.POINTER(rsf_shard_link)]),
     "rsf_shard_frame_device": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4,
                                          C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
+    "rsf_shard_feed_device": (C.c_int, [_P, _P]),
+    "rsf_shard_step_device": (C.c_int, [_P, C.c_float, _F4, _F4, C.c_float, _F4, _F4, _P, _P, _P, _P]),
+    "rsf_stream_wait_flag_device": (C.c_int, [_P, _P, C.c_uint32]),
+    "rsf_stream_wait_flag_on": (C.c_int, [C.c_int, _P, _P, C.c_uint32]),
     "rsf_synchronize": (C.c_int, [_P]),
     "rsf_num_active_blocks": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "rsf_get_stats": (C.c_int, [_P, C.POINTER(rsf_frame_stats)]),
@@ -366,12 +371,30 @@ class TSDFGrid:
                                                    ptr["depth"], ptr["prob"]))
         return out
 
-    def ShardSetLink(self, planes0: int, planes1: int, flags: int, n_planes: int, root: int, H: int, W: int, skip_mask: int = 0):
-        """rsf_shard_set_link: device addresses (in THIS process) of the presenting rank's merge planes / arrival flags."""
+    def ShardSetLink(self, planes0: int, planes1: int, flags: int, n_planes: int, root: int, H: int, W: int, skip_mask: int = 0,
+                     transport: dict | None = None):
+        """rsf_shard_set_link: device addresses (in THIS process) of the presenting rank's merge planes / arrival flags.
+        transport = {frame_H, frame_W, rx: [p0, p1], frame_flag: p, kids: [{rx: [p0, p1], flag: p}, ...]} enables the
+        in-library frame tree (ShardFeed / ShardStep)."""
         ln = rsf_shard_link()
         ln.planes[0], ln.planes[1], ln.flags = planes0, planes1, flags
         ln.n_planes, ln.root, ln.H, ln.W, ln.skip_mask = n_planes, root, H, W, skip_mask
+        if transport:
+            ln.frame_H, ln.frame_W = transport["frame_H"], transport["frame_W"]
+            ln.rx[0], ln.rx[1], ln.frame_flag = transport["rx"][0], transport["rx"][1], transport["frame_flag"]
+            ln.n_kids = len(transport["kids"])
+            for c, kid in enumerate(transport["kids"]):
+                ln.kid_rx[c][0], ln.kid_rx[c][1], ln.kid_flag[c] = kid["rx"][0], kid["rx"][1], kid["flag"]
         _check(self._lib.rsf_shard_set_link(self._h, C.byref(ln)))
+
+    def ShardFeed(self, packed_frame_ptr: int | None):
+        _check(self._lib.rsf_shard_feed_device(self._h, packed_frame_ptr))
+
+    def ShardStep(self, max_depth: float, K: np.ndarray, pose: np.ndarray, raycast_max_depth: float, rc_K: np.ndarray,
+                  rc_pose: np.ndarray, out_ptrs=(None, None, None, None)):
+        """rsf_shard_step_device with pre-built float32 arrays (K[4], pose[7]) and raw output pointers (rgba, normal, depth, prob)."""
+        _check(self._lib.rsf_shard_step_device(self._h, max_depth, _fptr(K), _fptr(pose), raycast_max_depth, _fptr(rc_K), _fptr(rc_pose),
+                                               *out_ptrs))
 
     def ShardFrame(self, img_rgb, img_depth, img_ht, img_lt, max_depth: float, intrinsics: CameraIntrinsics, cam_T_world: SE3,
                    raycast_max_depth: float, virtual_cam: CameraParams, rc_cam_T_world: SE3, out: dict | None = None):
@@ -387,6 +410,10 @@ class TSDFGrid:
                                                 virtual_cam.img_h, virtual_cam.img_w, _fptr(rK), _fptr(rpose),
                                                 ptr["rgba"], ptr["normal"], ptr["depth"], ptr["prob"]))
         return out
+
+    def StreamWaitFlag(self, flag_ptr: int, value: int):
+        """rsf_stream_wait_flag_device: the grid's stream waits (on the device) until *flag_ptr >= value."""
+        _check(self._lib.rsf_stream_wait_flag_device(self._h, flag_ptr, value))
 
     def synchronize(self):
         _check(self._lib.rsf_synchronize(self._h))
@@ -475,15 +502,15 @@ class TSDFGrid:
         _check(self._lib.rsf_get_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in rsf_frame_stats._fields_}
 
-    PROF_KERNELS = ("allocate", "select", "integrate", "raycast")
+    PROF_KERNELS = ("allocate", "select", "integrate", "raycast", "merge")
 
     def profile_enable(self, on: bool = True):
         _check(self._lib.rsf_profile_enable(self._h, int(on)))
 
     def profile_read(self) -> dict:
         """{kernel: (total_ms, launches)} since the last read."""
-        ms = (C.c_double * 4)()
-        n = (C.c_int64 * 4)()
+        ms = (C.c_double * len(self.PROF_KERNELS))()
+        n = (C.c_int64 * len(self.PROF_KERNELS))()
         _check(self._lib.rsf_profile_read(self._h, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_KERNELS)}
 
@@ -553,6 +580,11 @@ class TSDFGrid:
         out = np.empty(len(p), np.float32)
         _check(self._lib.rsf_retrieve_tsdf_trilinear(self._h, p.ctypes.data, len(p), out.ctypes.data))
         return out
+
+
+def stream_wait_flag(device: int, stream: int, flag_ptr: int, value: int):
+    """rsf_stream_wait_flag_on: cudaStream_t `stream` of `device` waits (on the device) until *flag_ptr >= value."""
+    _check(load_library().rsf_stream_wait_flag_on(device, stream or None, flag_ptr, value))
 
 
 def block_keys(coords: np.ndarray) -> np.ndarray:

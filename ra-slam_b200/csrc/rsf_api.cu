@@ -5,6 +5,7 @@
 // streams, 4 host synchronisations and 2 synchronous D2H counter reads; here a
 // frame is 4 H2D copies + 1 memset + 3 launches on one stream and, for the blocking host entry
 // point, one 128-byte counter read-back and one synchronisation.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -96,6 +97,11 @@ struct rsf_grid_s {
   rsf_shard_link link{};
   bool linked = false;
   unsigned shard_seq = 0;
+  // in-library frame transport (rsf_shard_feed_device / rsf_shard_step_device)
+  cudaStream_t kid_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_step_done[2] = {nullptr, nullptr};   // recorded on `stream` after the step of that frame parity
+  unsigned fed = 0, stepped = 0;
+  const uint8_t* fed_src[2] = {nullptr, nullptr};     // ingest rank: the caller's packed frame of that parity
   // optional per-kernel CUDA-event timing (rsf_profile_*)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[RSF_PROF_NUM];
@@ -414,6 +420,10 @@ int rsf_destroy(rsf_grid_t g) {
     if (sl.ready) cudaEventDestroy(sl.ready);
     if (sl.done) cudaEventDestroy(sl.done);
   }
+  for (auto& st : g->kid_stream)
+    if (st) cudaStreamDestroy(st);
+  for (auto& e : g->ev_step_done)
+    if (e) cudaEventDestroy(e);
   if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
   if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
   if (g->s_side) cudaStreamDestroy(g->s_side);
@@ -614,6 +624,54 @@ int rsf_merge_finalize_device(rsf_grid_t g, int H, int W, uint64_t* merge_planes
   return RSF_OK;
 }
 
+static int stream_wait_flag(cudaStream_t stream, const uint32_t* flag, uint32_t value) {
+  typedef CUresult (*wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static wait32_fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (wait32_fn)p;
+  }();
+  if (fn && fn((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS) return RSF_OK;
+  launch_shard_wait(flag, 1, value, stream);   // polling kernel
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+// *flag = value, ordered after everything already on `stream`; a stream memory operation (no SM), else a 32-bit memset
+static int stream_write_flag(cudaStream_t stream, uint32_t* flag, uint32_t value) {
+  typedef CUresult (*write32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  typedef CUresult (*memset32_fn)(CUdeviceptr, unsigned int, size_t, CUstream);
+  static write32_fn wfn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (write32_fn)p;
+  }();
+  static memset32_fn mfn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemsetD32Async", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (memset32_fn)p;
+  }();
+  if (wfn && wfn((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) return RSF_OK;
+  if (mfn && mfn((CUdeviceptr)(uintptr_t)flag, value, 1, (CUstream)stream) == CUDA_SUCCESS) return RSF_OK;
+  return fail(RSF_ERR_CUDA, "neither cuStreamWriteValue32 nor cuMemsetD32Async could write the frame flag");
+}
+
+int rsf_stream_wait_flag_device(rsf_grid_t g, const uint32_t* flag, uint32_t value) {
+  if (int rc = check_grid(g)) return rc;
+  if (!flag) return fail(RSF_ERR_INVALID, "flag must not be NULL");
+  DeviceGuard dg(g->device);
+  return stream_wait_flag(g->stream, flag, value);
+}
+
+int rsf_stream_wait_flag_on(int device, void* stream, const uint32_t* flag, uint32_t value) {
+  if (!flag) return fail(RSF_ERR_INVALID, "flag must not be NULL");
+  DeviceGuard dg(device);
+  return stream_wait_flag((cudaStream_t)stream, flag, value);
+}
+
 int rsf_shard_set_link(rsf_grid_t g, const rsf_shard_link* link) {
   if (int rc = check_grid(g)) return rc;
   if (!link) {
@@ -626,9 +684,77 @@ int rsf_shard_set_link(rsf_grid_t g, const rsf_shard_link* link) {
   if (g->opt.shard_world > 32) return fail(RSF_ERR_INVALID, "rsf_shard_frame_device supports shard_world <= 32");
   if (link->H <= 0 || link->W <= 0) return fail(RSF_ERR_INVALID, "H, W must be > 0");
   if (link->skip_mask & ~6u) return fail(RSF_ERR_INVALID, "skip_mask may only name planes 1 and 2");
+  if (link->rx[0]) {
+    if (!link->rx[1] || !link->frame_flag || link->frame_H <= 0 || link->frame_W <= 0 || link->n_kids < 0 || link->n_kids > 2)
+      return fail(RSF_ERR_INVALID, "frame transport: rx[2], frame_flag, frame_H / frame_W and 0 <= n_kids <= 2 are required");
+    if ((size_t)link->frame_H * (size_t)link->frame_W > g->max_pixels) return fail(RSF_ERR_INVALID, "frame size exceeds max_pixels");
+    if (((size_t)link->frame_H * link->frame_W * 3) % 4) return fail(RSF_ERR_INVALID, "packed frames need 3 H W divisible by 4");
+    for (int c = 0; c < link->n_kids; ++c)
+      if (!link->kid_rx[c][0] || !link->kid_rx[c][1] || !link->kid_flag[c]) return fail(RSF_ERR_INVALID, "kid_rx / kid_flag missing");
+    DeviceGuard dg(g->device);
+    for (int c = 0; c < 2; ++c) {
+      if (!g->kid_stream[c]) RSF_CUDA(cudaStreamCreateWithFlags(&g->kid_stream[c], cudaStreamNonBlocking));
+      if (!g->ev_step_done[c]) RSF_CUDA(cudaEventCreateWithFlags(&g->ev_step_done[c], cudaEventDisableTiming));
+    }
+  }
   g->link = *link;
   g->linked = true;
   g->shard_seq = 0;
+  g->fed = g->stepped = 0;
+  return RSF_OK;
+}
+
+int rsf_shard_feed_device(rsf_grid_t g, const uint8_t* packed_frame) {
+  if (int rc = check_grid(g)) return rc;
+  if (!g->linked || !g->link.rx[0]) return fail(RSF_ERR_INVALID, "rsf_shard_set_link with a frame transport has not been called");
+  if (g->fed - g->stepped >= 2) return fail(RSF_ERR_INVALID, "two frames are already in flight: call rsf_shard_step_device first");
+  const rsf_shard_link& L = g->link;
+  const bool ingest = g->opt.shard_rank == L.root;
+  if (ingest && !packed_frame) return fail(RSF_ERR_INVALID, "packed_frame must not be NULL on the ingest rank");
+  DeviceGuard dg(g->device);
+  const unsigned seq = g->fed + 1;
+  const int j = (int)(g->fed & 1u);
+  const size_t nbytes = (size_t)15 * L.frame_H * L.frame_W;
+  const uint8_t* src = ingest ? packed_frame : L.rx[j];
+  g->fed_src[j] = src;
+  for (int c = 0; c < L.n_kids; ++c) {
+    cudaStream_t st = g->kid_stream[c];
+    if (ingest) {
+      // frame seq - 2 is through on every rank (its arrival flags were awaited by my step): buffers j are free
+      if (g->fed >= 2) RSF_CUDA(cudaStreamWaitEvent(st, g->ev_step_done[j], 0));
+    } else {
+      if (int rc = stream_wait_flag(st, L.frame_flag + j, seq)) return rc;      // my own copy has landed
+    }
+    RSF_CUDA(cudaMemcpyAsync(L.kid_rx[c][j], src, nbytes, cudaMemcpyDeviceToDevice, st));   // data first ...
+    if (int rc = stream_write_flag(st, L.kid_flag[c] + j, seq)) return rc;                  // ... then its sequence number
+  }
+  ++g->fed;
+  return RSF_OK;
+}
+
+int rsf_shard_step_device(rsf_grid_t g, float max_depth, const float K[4], const float pose[7], float raycast_max_depth,
+                          const float rc_K[4], const float rc_pose[7], uint8_t* rgba, uint8_t* normal, float* depth_out,
+                          float* prob_out) {
+  if (int rc = check_grid(g)) return rc;
+  if (!g->linked || !g->link.rx[0]) return fail(RSF_ERR_INVALID, "rsf_shard_set_link with a frame transport has not been called");
+  if (g->stepped >= g->fed) return fail(RSF_ERR_INVALID, "rsf_shard_step_device without a fed frame");
+  const rsf_shard_link& L = g->link;
+  const int j = (int)(g->stepped & 1u);
+  const unsigned seq = g->stepped + 1;
+  const uint8_t* src = g->fed_src[j];
+  {
+    DeviceGuard dg(g->device);
+    if (g->opt.shard_rank != L.root)
+      if (int rc = stream_wait_flag(g->stream, L.frame_flag + j, seq)) return rc;           // the frame is in rx[j]
+  }
+  const size_t P = (size_t)L.frame_H * L.frame_W;
+  const int rc = rsf_shard_frame_device(g, src, reinterpret_cast<const float*>(src + 3 * P), reinterpret_cast<const float*>(src + 7 * P),
+                                        reinterpret_cast<const float*>(src + 11 * P), L.frame_H, L.frame_W, max_depth, K, pose,
+                                        raycast_max_depth, L.H, L.W, rc_K, rc_pose, rgba, normal, depth_out, prob_out);
+  if (rc) return rc;
+  DeviceGuard dg(g->device);
+  RSF_CUDA(cudaEventRecord(g->ev_step_done[j], g->stream));
+  ++g->stepped;
   return RSF_OK;
 }
 
@@ -665,6 +791,7 @@ int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float* depth,
   }
   launch_shard_signal(g->link.flags + rank, seq, g->stream);
   if (rank == g->link.root) {
+    ProfScope p(g, RSF_PROF_MERGE);
     launch_shard_wait(g->link.flags, world, seq, g->stream);
     launch_merge_finalize(planes, plane_spec, rc_H * rc_W, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
                           depth_out, prob_out, g->sm_count, g->stream);

@@ -167,21 +167,35 @@ class FusedMinDepthMerge:
 class ShardedScene:
     """One large scene spatially sharded over the GPUs of a box, driven with ONE C-ABI call per frame per rank.
 
-    Per frame: the ingest rank's packed frame is broadcast with one NCCL collective (``feed``, on a side stream, so the
-    transfer of frame k + 1 overlaps the kernels of frame k), then every rank calls ``rsf_shard_frame_device`` (``step``,
-    C++): allocate (ownership first) | select -> integrate -> tile ranges -> raycast with the min-depth merge fused in
-    (system-scope atomicMin into the presenting rank's planes over NVLink peer memory) -> arrival flag (release, system
-    scope) in the presenting rank's memory; the presenting rank's stream then waits for all flags on the device and
-    unpacks the planes.  No host-side barrier, no Python between the kernels.
+    Per frame: the ingest rank's packed frame reaches every rank (``feed``), then every rank calls
+    ``rsf_shard_frame_device`` (``step``, C++): allocate (ownership first) | select -> integrate -> tile ranges -> raycast
+    with the min-depth merge fused in (system-scope atomicMin into the presenting rank's planes over NVLink peer memory)
+    -> arrival flag (release, system scope) in the presenting rank's memory; the presenting rank's stream then waits for all
+    flags on the device and unpacks the planes.  No host-side barrier, no Python between the kernels.
+
+    Frame transport, ``transport=``:
+      "p2p"  (default) a binary tree of copy-engine pushes rooted at the ingest rank: a rank's copy engines push the frame
+             from its receive buffer into its (at most two) children's receive buffers (symmetric memory, NVLink peer
+             writes, one stream per child) followed by a 4-byte sequence word; forwarding and the compute stream wait
+             for that word with a stream memory operation (rsf_stream_wait_flag_*).  No SM is involved, so the transfer
+             of frame k + 1 really overlaps the kernels of frame k -- an NCCL kernel cannot: the fusion kernels are
+             persistent grids that fill every SM, and the collective's CTAs only get in when a kernel ends (measured:
+             90 us of every 0.3 ms step waiting for the broadcast at 8 ranks, 350 us without idle gaps between steps).
+             A star (the ingest rank pushing to all seven peers, one after the other) is bound by its own egress: 7 x
+             ~60 us per 18.8 MB frame made the pushes, not the kernels, the cycle time at 8 ranks.
+      "nccl" one ncclBroadcast per frame on a side stream (the NCCL data plane; kept for comparison).
     Receive buffers and merge planes are double-buffered by frame parity: ``feed`` of frame k + 2 waits (stream event) for
-    ``step`` of frame k on the same rank, which on the presenting rank includes the re-arming of that frame's planes --
-    so nobody can write a plane set before it has been re-armed (rsfusion.h, rsf_shard_link).
+    ``step`` of frame k on the ingest / presenting rank, which includes the device-side wait for every rank's arrival flag
+    of frame k -- so by then every rank has consumed frame k's buffer and nobody can write a plane set before it has been
+    re-armed (rsfusion.h, rsf_shard_link).  The ingest rank must be the presenting rank (`root`).
     """
 
     def __init__(self, voxel_size: float, truncation: float, H: int, W: int, device, *, root: int = 0, outputs=("rgba", "depth", "prob"),
-                 group=None, pool_blocks: int = 0, table_slots_log2: int = 0, shard_shift: int = 4, shard_halo: int = 1):
+                 group=None, pool_blocks: int = 0, table_slots_log2: int = 0, shard_shift: int = 4, shard_halo: int = 1,
+                 transport: str = "p2p"):
         from . import TSDFGrid
-        self.H, self.W, self.root = H, W, root
+        assert transport in ("p2p", "nccl")
+        self.H, self.W, self.root, self.transport = H, W, root, transport
         n_planes = 3
         self.dist_on = dist.is_available() and dist.is_initialized()
         self.group = group if group is not None else (dist.group.WORLD if self.dist_on else None)
@@ -192,42 +206,67 @@ class ShardedScene:
         self.grid = TSDFGrid(voxel_size, truncation, device=self.device.index, pool_blocks=pool_blocks,
                              table_slots_log2=table_slots_log2, shard_rank=self.rank, shard_world=self.world,
                              shard_shift=shard_shift, shard_halo=shard_halo, stream=self.stream.cuda_stream)
-        self.rx = [torch.empty(frame_nbytes(H, W), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.nbytes = frame_nbytes(H, W)
         self.fed = [None, None]
         self.side = torch.cuda.Stream(self.device)
         self.ev_feed = [torch.cuda.Event() for _ in range(2)]
         self.ev_done = [torch.cuda.Event() for _ in range(2)]
         self.n_fed = self.n_stepped = 0
+        self.stall_events = None
         self.sym = None
         if self.world > 1:
             import torch.distributed._symmetric_memory as symm_mem
             P = H * W
-            words = 2 * n_planes * P + 64                    # two plane sets + the arrival flags (32-bit words inside)
-            self.sym = symm_mem.empty(words, dtype=torch.int64, device=self.device)
-            self.sym.fill_(-1)
-            self.sym[2 * n_planes * P:].zero_()
+            # symmetric allocation, in 64-bit words: [2 plane sets | arrival flags (64) | frame flags (64) | rx0 | rx1]
+            w_planes = 2 * n_planes * P
+            w_rx = (self.nbytes + 7) // 8
+            self.sym = symm_mem.empty(w_planes + 128 + 2 * w_rx, dtype=torch.int64, device=self.device)
+            self.sym[:w_planes].fill_(-1)
+            self.sym[w_planes:].zero_()
             self.hdl = symm_mem.rendezvous(self.sym, self.group)
             base = int(self.hdl.buffer_ptrs[root])
             skip = (0 if "normal" in outputs else 2) | (0 if "prob" in outputs else 4)
-            self.grid.ShardSetLink(base, base + 8 * n_planes * P, base + 16 * n_planes * P, n_planes, root, H, W, skip)
+            off_fflag = 8 * (w_planes + 64)
+            off_rx = [8 * (w_planes + 128), 8 * (w_planes + 128 + w_rx)]
+            mine = self.sym.view(torch.uint8)
+            self.rx = [mine[off_rx[j]:off_rx[j] + self.nbytes] for j in range(2)]
+            self.fflag_ptr = [int(self.hdl.buffer_ptrs[self.rank]) + off_fflag + 4 * j for j in range(2)]
+            tr = None
+            if transport == "p2p":
+                me = (self.rank - root) % self.world         # position in the tree: children of node i are 2i + 1, 2i + 2
+                kids = [(root + c) % self.world for c in (2 * me + 1, 2 * me + 2) if c < self.world]
+                ptr = lambda r: int(self.hdl.buffer_ptrs[r])
+                tr = {"frame_H": H, "frame_W": W, "rx": [ptr(self.rank) + off_rx[0], ptr(self.rank) + off_rx[1]],
+                      "frame_flag": ptr(self.rank) + off_fflag,
+                      "kids": [{"rx": [ptr(r) + off_rx[0], ptr(r) + off_rx[1]], "flag": ptr(r) + off_fflag} for r in kids]}
+            self.grid.ShardSetLink(base, base + 8 * n_planes * P, base + 8 * w_planes, n_planes, root, H, W, skip, transport=tr)
             torch.cuda.synchronize(self.device)
             self.hdl.barrier()                               # everyone's planes are armed before the first frame
+        else:
+            self.rx = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
 
     def feed(self, packed_frame=None):
         """All ranks.  Start moving the next frame: `packed_frame` is the uint8 tensor in `pack_frame` layout on the ingest
-        rank (None elsewhere).  Returns at once; the broadcast runs on a side stream."""
+        rank (None elsewhere).  Returns at once; the transfer runs on copy engines / a side stream."""
         j = self.n_fed & 1
         if self.rank == self.root:
-            assert packed_frame is not None and packed_frame.numel() == self.rx[j].numel()
+            assert packed_frame is not None and packed_frame.numel() == self.nbytes
+        if self.world > 1 and self.transport == "p2p":       # the library's copy-engine tree (rsf_shard_feed_device)
+            self.fed[j] = packed_frame                       # keep the ingest rank's frame alive until it is consumed
+            self.grid.ShardFeed(packed_frame.data_ptr() if self.rank == self.root else None)
+            self.n_fed += 1
+            return
         with torch.cuda.stream(self.side):
             if self.n_fed >= 2:
-                self.side.wait_event(self.ev_done[j])        # frame n_fed - 2 is through: buffer j and plane set j are free
+                self.side.wait_event(self.ev_done[j])        # frame n_fed - 2 is through on every rank: buffers j are free
             else:
                 self.side.wait_stream(self.stream)
-            src = packed_frame if self.rank == self.root else self.rx[j]
-            if self.world > 1:
+            if self.world > 1 and self.transport == "nccl":
+                src = packed_frame if self.rank == self.root else self.rx[j]
                 dist.broadcast(src, src=self.root, group=self.group, async_op=True).wait()
-            self.fed[j] = src
+                self.fed[j] = src
+            else:
+                self.fed[j] = packed_frame if self.rank == self.root else self.rx[j]
             self.ev_feed[j].record(self.side)
         self.n_fed += 1
 
@@ -238,7 +277,18 @@ class ShardedScene:
         assert torch.cuda.current_stream(self.device).cuda_stream == self.stream.cuda_stream, \
             "ShardedScene must be stepped on the stream it was created on"
         j = self.n_stepped & 1
+        if self.world > 1 and self.transport == "p2p":       # rsf_shard_step_device: device-side wait for the frame + the fused frame
+            o = out if (out is not None and self.rank == self.root) else {}
+            ptrs = tuple(o[k].data_ptr() if k in o else None for k in ("rgba", "normal", "depth", "prob"))
+            self.grid.ShardStep(max_depth, intrinsics.as_array(), cam_T_world.as_array(), raycast_max_depth,
+                                virtual_cam.intrinsics.as_array(), rc_cam_T_world.as_array(), ptrs)
+            self.n_stepped += 1
+            return out if self.rank == self.root else None
         self.stream.wait_event(self.ev_feed[j])
+        if self.stall_events is not None:                # measurement hook: when did the frame's data become available?
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(self.stream)
+            self.stall_events.append(e)
         fr = unpack_frame(self.fed[j], self.H, self.W)
         self.grid.ShardFrame(*fr, max_depth, intrinsics, cam_T_world, raycast_max_depth, virtual_cam, rc_cam_T_world,
                              out if self.rank == self.root else None)
