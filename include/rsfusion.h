@@ -169,6 +169,13 @@ RSF_API int rsf_wait(rsf_grid_t g, int ticket);
 RSF_API int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
                        uint8_t* rgba, uint8_t* normal, float* depth, float* prob);
 
+/* TSDFGrid::RayCast as the reference's callers use it (GLImage8UC4::LoadCuda takes a CUDA pointer, voxel_tsdf.cu:895-900):
+ * render into the grid's OWN device images (the reference's img_tsdf_rgba_ / img_tsdf_normal_) and return their device
+ * addresses and the cudaStream_t (as void*) the kernel was enqueued on.  The images are valid until the next raycast on
+ * this grid; the call does not wait for the kernel. */
+RSF_API int rsf_raycast_internal_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7],
+                                        const uint8_t** rgba_dev, const uint8_t** normal_dev, void** stream);
+
 /* Spatially sharded grids (rsf_options.shard_world > 1): raycast with the per-pixel min-depth merge fused into the
  * kernel (new; the reference is single-GPU).  merge_planes points to n_planes * H * W 64-bit words preset to all-ones --
  * normally the PRESENTING rank's buffer, mapped into this process as NVLink peer memory (torch symmetric memory,

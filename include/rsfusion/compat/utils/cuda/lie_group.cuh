@@ -1,0 +1,4 @@
+// Include overlay for the reference's utils/cuda/lie_group.cuh: the types live in rsfusion/tsdf_grid.hpp (see
+// utils/tsdf/voxel_tsdf.cuh in this directory).
+#pragma once
+#include "utils/tsdf/voxel_tsdf.cuh"

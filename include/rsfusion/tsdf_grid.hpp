@@ -34,7 +34,9 @@
 #include <Eigen/Geometry>
 #endif
 #ifdef RSFUSION_WITH_OPENCV
+#ifndef CV_8UC3          // (an overlay build has included <opencv2/opencv.hpp> already)
 #include <opencv2/core.hpp>
+#endif
 #endif
 
 namespace rsfusion {
@@ -244,9 +246,29 @@ class TSDFGrid {
   }
   void Synchronize() { check(rsf_synchronize(g_)); }
 
+#ifdef RSFUSION_WITH_GL
+  // The reference's signature (voxel_tsdf.cuh:78-79): render into the grid's device images and hand them to the OpenGL
+  // bridge, GLImage8UC4::LoadCuda(device pointer, stream), exactly as voxel_tsdf.cu:895-901 does; then synchronise.
+  // GLImage8UC4 comes from the caller's utils/gl/image.h, which must be included before this header.
+  void RayCast(float max_depth, const CameraParams& virtual_cam, const SE3<float>& cam_T_world, GLImage8UC4* tsdf_rgba = NULL,
+               GLImage8UC4* tsdf_normal = NULL) {
+    const float K[4] = {virtual_cam.intrinsics.fx, virtual_cam.intrinsics.fy, virtual_cam.intrinsics.cx, virtual_cam.intrinsics.cy};
+    const auto pose = cam_T_world.as_pose();
+    const uint8_t *d_rgba = nullptr, *d_normal = nullptr;
+    void* stream = nullptr;
+    check(rsf_raycast_internal_device(g_, max_depth, virtual_cam.img_h, virtual_cam.img_w, K, pose.data(), &d_rgba, &d_normal, &stream));
+    if (tsdf_rgba != NULL) tsdf_rgba->LoadCuda(d_rgba, (cudaStream_t)stream);
+    if (tsdf_normal != NULL) tsdf_normal->LoadCuda(d_normal, (cudaStream_t)stream);
+    check(rsf_synchronize(g_));
+  }
+  // host-buffer form (no defaults here, so that RayCast(max_depth, cam, pose) is the reference's call)
+  void RayCast(float max_depth, const CameraParams& virtual_cam, const SE3<float>& cam_T_world, uint8_t* tsdf_rgba,
+               uint8_t* tsdf_normal, float* depth = nullptr, float* prob = nullptr) {
+#else
   // voxel_tsdf.cu:885-902.  rgba / normal: img_h*img_w*4 bytes each; depth / prob: img_h*img_w floats.
   void RayCast(float max_depth, const CameraParams& virtual_cam, const SE3<float>& cam_T_world, uint8_t* tsdf_rgba = nullptr,
                uint8_t* tsdf_normal = nullptr, float* depth = nullptr, float* prob = nullptr) {
+#endif
     const float K[4] = {virtual_cam.intrinsics.fx, virtual_cam.intrinsics.fy, virtual_cam.intrinsics.cx, virtual_cam.intrinsics.cy};
     const auto pose = cam_T_world.as_pose();
     check(rsf_raycast(g_, max_depth, virtual_cam.img_h, virtual_cam.img_w, K, pose.data(), tsdf_rgba, tsdf_normal, depth, prob));
@@ -273,6 +295,25 @@ class TSDFGrid {
     vertex_prob_buffer->resize((size_t)nv);
     index_buffer->resize((size_t)nt);
   }
+
+#ifdef RSFUSION_WITH_EIGEN
+  // The reference's signature (voxel_tsdf.cuh:104-106); Eigen::Vector3f / Vector3i are three packed 32-bit words.
+  void GatherValidMesh(std::vector<Eigen::Vector3f>* vertex_buffer, std::vector<Eigen::Vector3i>* index_buffer,
+                       std::vector<float>* vertex_prob_buffer) {
+    static_assert(sizeof(Eigen::Vector3f) == 12 && sizeof(Eigen::Vector3i) == 12, "packed 3-vectors expected");
+    int64_t nv = 0, nt = 0;
+    check(rsf_gather_valid_mesh(g_, nullptr, 0, &nv, nullptr, 0, &nt, nullptr));
+    vertex_buffer->resize((size_t)nv);
+    vertex_prob_buffer->resize((size_t)nv);
+    index_buffer->resize((size_t)nt);
+    if (nv || nt)
+      check(rsf_gather_valid_mesh(g_, reinterpret_cast<float*>(vertex_buffer->data()), nv, &nv,
+                                  reinterpret_cast<int32_t*>(index_buffer->data()), nt, &nt, vertex_prob_buffer->data()));
+    vertex_buffer->resize((size_t)nv);
+    vertex_prob_buffer->resize((size_t)nv);
+    index_buffer->resize((size_t)nt);
+  }
+#endif
 
   int NumActiveBlock() {   // hash_table_.NumActiveBlock(), voxel_hash.cu:225
     int64_t n = 0;

@@ -129,10 +129,25 @@ class TSDFSystem {
     pause_ = pause;
     cv_pause_.notify_all();
   }
-  // Block until every queued frame has been integrated (new; the reference has no such call).
+  // Block until every queued frame has been integrated (new; the reference has no such call).  Throws if a frame was
+  // dropped because of an error since the last Flush (pool exhausted, CUDA error): the reference would have aborted.
   void Flush() {
     std::unique_lock<std::mutex> lock(mtx_queue_);
-    cv_free_.wait(lock, [&] { return free_.size() == slots_.size() || worker_dead_; });
+    cv_free_.wait(lock, [&] { return (inputs_.empty() && free_.size() >= slots_.size()) || worker_dead_; });
+    if (dropped_frames_ > 0) {
+      const std::string msg = last_error_;
+      dropped_frames_ = 0;
+      throw Error(RSF_ERR_CUDA, "TSDFSystem: frame(s) dropped: " + msg);
+    }
+  }
+  // message of the most recent worker-thread error ("" if none) and the number of frames dropped since the last Flush
+  std::string last_error() {
+    std::lock_guard<std::mutex> lock(mtx_queue_);
+    return last_error_;
+  }
+  int dropped_frames() {
+    std::lock_guard<std::mutex> lock(mtx_queue_);
+    return dropped_frames_;
   }
   TSDFGrid& grid() { return tsdf_; }
 
@@ -168,6 +183,7 @@ class TSDFSystem {
         slot = inputs_.front();
         inputs_.pop_front();
       }
+      bool queued = false;     // has `slot` joined in_flight?  (decides who recycles it on an error)
       try {
         std::lock_guard<std::mutex> lock(mtx_read_);
         Slot& s = slots_[slot];
@@ -175,6 +191,7 @@ class TSDFSystem {
                              Image(s.ht, s.rows, s.cols, kType32FC1), Image(s.lt, s.rows, s.cols, kType32FC1), max_depth_,
                              intrinsics_, s.cam_T_world);
         in_flight.push_back(slot);
+        queued = true;
         bool idle;
         {
           std::lock_guard<std::mutex> ql(mtx_queue_);
@@ -189,9 +206,15 @@ class TSDFSystem {
           cv_free_.notify_all();
         }
       } catch (const std::exception& e) {
-        last_error_ = e.what();
+        // A pool-full / CUDA error usually surfaces in Synchronize(), i.e. after `slot` has joined in_flight: recycle every
+        // slot exactly once, and only after the copy engine can no longer be reading any of them (best effort: the
+        // stream may itself be in error).  The reference aborts here (CUDA_SAFE_CALL); we keep running and keep the
+        // message for last_error() / Flush().
+        rsf_synchronize(tsdf_.handle());
         std::lock_guard<std::mutex> ql(mtx_queue_);
-        free_.push_back(slot);
+        last_error_ = e.what();
+        ++dropped_frames_;
+        if (!queued) free_.push_back(slot);
         for (int f : in_flight) free_.push_back(f);
         in_flight.clear();
         cv_free_.notify_all();
@@ -215,7 +238,8 @@ class TSDFSystem {
   std::mutex mtx_pause_;
   std::condition_variable cv_pause_;
   bool pause_ = false;
-  std::string last_error_;
+  std::string last_error_;   // guarded by mtx_queue_
+  int dropped_frames_ = 0;
   std::thread t_;
 };
 

@@ -78,6 +78,7 @@ ABI = {
     "rsf_gather_valid_classes": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "rsf_raycast": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
+    "rsf_raycast_internal_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "rsf_raycast_merge_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, C.c_int]),
     "rsf_merge_finalize_device": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
     "rsf_shard_set_link": (C.c_int, [_P, C.POINTER(rsf_shard_link)]),

@@ -126,7 +126,8 @@ struct Counters {
   // running totals over all frames (folded in by begin_frame_kernel); used by the benchmark
   unsigned long long tot_frames, tot_new_blocks, tot_visible_blocks, tot_updated_voxels, tot_carved_blocks;
   unsigned ray_work;   // next 8x4 pixel patch of the persistent raycast kernel
-  unsigned pad3[7];
+  unsigned ray_work2;  // same for the second row band of a banded raycast (rsf_raycast to host buffers)
+  unsigned pad3[6];
 };
 static_assert(sizeof(Counters) == 128, "Counters must stay one 128-byte line");
 constexpr size_t kCtrFrameOff = 16, kCtrFrameBytes = 32, kCtrGatherOff = 48;

@@ -29,6 +29,12 @@ size_t raycast_ranges_bytes(int W, int H);
 void launch_raycast(const GridView& g, const Frame& f, float step_size, unsigned* ranges, uchar4* rgba, uchar4* normal,
                     float* depth, float* prob, int sm_count, cudaStream_t s, unsigned long long* merge = nullptr,
                     int merge_planes = 0);
+// the same in two steps: the per-tile pre-pass once, then one launch per band of 4-pixel patch rows (band = 0 / 1 picks
+// the work queue); the host path renders two bands so the read-back of the first overlaps the march of the second
+void launch_raycast_prepass(const GridView& g, const Frame& f, float step_size, unsigned* ranges, int sm_count, cudaStream_t s);
+void launch_raycast_band(const GridView& g, const Frame& f, float step_size, const unsigned* ranges, uchar4* rgba, uchar4* normal,
+                         float* depth, float* prob, int sm_count, cudaStream_t s, int patch_row0, int patch_rows, int band,
+                         unsigned long long* merge = nullptr, int merge_planes = 0);
 void launch_merge_finalize(unsigned long long* merge, int merge_planes, int P, uchar4* rgba, uchar4* normal, float* depth,
                            float* prob, int sm_count, cudaStream_t s);
 // sharded frame: arrival flags in the presenting rank's memory (system-scope release / acquire)
