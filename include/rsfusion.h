@@ -136,6 +136,17 @@ RSF_API int rsf_integrate_u16_device(rsf_grid_t g, const uint8_t* rgb, const uin
                                      const uint16_t* lt, int H, int W, float depth_factor, float max_depth,
                                      const float K[4], const float pose[7]);
 
+/* cv::resize(src, dst, cv::Size(dst_W, dst_H)) with its default INTER_LINEAR, on the grid's device and stream (new;
+ * GPU-side input preparation).  The reference's callers resize every frame on the CPU before TSDFGrid::Integrate:
+ * disinfect_slam/disinfect_slam.cc:37-38 (rgb 8UC3 and the raw 16UC1 depth down to the TSDF size),
+ * utils/offline_data_provider/scannet_sens_reader.cc:78 (1296x968 colour -> 640x480), segmentation/inference.cc:28 (32FC1
+ * probability maps).  Formats: channels = 3 with elem_bytes = 1 (8UC3); channels = 1 with elem_bytes = 1, 2 or 4 (8UC1,
+ * 16UC1, 32FC1).  Results equal OpenCV's portable code path bit for bit for the 8- and 16-bit types (fixed-point /
+ * float weights as in imgproc/resize.cpp; exact 2x decimation is the 2x2 mean cv::resize switches to).  src and dst are
+ * device pointers to continuous images; asynchronous on the grid's stream. */
+RSF_API int rsf_resize_device(rsf_grid_t g, const void* src, int src_H, int src_W, void* dst, int dst_H, int dst_W,
+                              int channels, int elem_bytes);
+
 /* K-class semantic fusion (extension; rsf_options.num_classes = K > 2).  The reference fuses two planes, ht and lt
  * (voxel_tsdf.cu:241-248); its K-class form is
  *   p_k <- exp((w_old ln p_k + w_new ln q_k) / w) / sum_j exp((w_old ln p_j + w_new ln q_j) / w)
@@ -295,6 +306,14 @@ RSF_API uint32_t rsf_shard_owner(int16_t x, int16_t y, int16_t z, int shift, int
 RSF_API int rsf_allocate_blocks(rsf_grid_t g, const int16_t* block_coords, int n);
 /* VoxelHashTable::Delete for n block coordinates. */
 RSF_API int rsf_delete_blocks(rsf_grid_t g, const int16_t* block_coords, int n);
+/* Table hygiene (new).  Carved blocks leave their key behind ("ghost"; VoxelHashTable::Delete, voxel_hash.cu:110-159,
+ * unlinks entries instead), so probe chains grow on a long session.  The library rebuilds the table from the alive-block
+ * list by itself, between two frames, when ghosts exceed 1/8 of the slots or the load 3/4 (rsf_frame_stats.table_keys /
+ * .table_rebuilds report it; a frame that returned RSF_ERR_TABLE_FULL forces one, so that error is recoverable).  This
+ * call forces a rebuild now.  Block contents and pool indices are untouched. */
+RSF_API int rsf_rebuild_table(rsf_grid_t g);
+/* Rebuild as soon as more than max_ghosts ghost keys are known to exist (capped at slots / 8; 0 = the default). */
+RSF_API int rsf_set_table_policy(rsf_grid_t g, int64_t max_ghosts);
 /* VoxelHashTable::Retrieve<VoxelTSDF|VoxelRGBW|VoxelSEGM> at n voxel coordinates (n x 3 i16).
  * found[i] = 1 if the voxel's block is allocated, else 0 and the reference's miss defaults are
  * returned (tsdf -10, rgbw 0, prob 0; voxel_types.cu:3,8,11).  Outputs may be NULL. */

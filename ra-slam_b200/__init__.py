@@ -76,6 +76,7 @@ ABI = {
     "rsf_integrate_classes": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
     "rsf_integrate_classes_device": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _F4, _F4]),
     "rsf_gather_valid_classes": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "rsf_resize_device": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rsf_raycast": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, _P, _P, _P, _P]),
     "rsf_raycast_internal_device": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _F4, _F4, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
@@ -101,6 +102,8 @@ ABI = {
     "rsf_shard_owner": (C.c_uint32, [C.c_int16, C.c_int16, C.c_int16, C.c_int, C.c_int]),
     "rsf_allocate_blocks": (C.c_int, [_P, _P, C.c_int]),
     "rsf_delete_blocks": (C.c_int, [_P, _P, C.c_int]),
+    "rsf_rebuild_table": (C.c_int, [_P]),
+    "rsf_set_table_policy": (C.c_int, [_P, C.c_int64]),
     "rsf_retrieve_voxels": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "rsf_assign_voxels": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
     "rsf_retrieve_tsdf_trilinear": (C.c_int, [_P, _P, C.c_int, _P]),
@@ -283,6 +286,10 @@ class TSDFGrid:
         if getattr(self, "_h", None):
             self._lib.rsf_destroy(self._h)
             self._h = None
+        pa = getattr(self, "_pinned_rows", None)
+        if pa is not None:
+            pa.free()
+            self._pinned_rows = None
 
     def __del__(self):
         try:
@@ -354,9 +361,9 @@ class TSDFGrid:
             _check(self._lib.rsf_integrate_classes(self._h, img_rgb.ctypes.data, img_depth.ctypes.data, class_prob.ctypes.data,
                                                    H, W, max_depth, _fptr(K), _fptr(pose)))
 
-    def GatherValidClasses(self) -> np.ndarray:
+    def GatherValidClasses(self, pinned: bool = False) -> np.ndarray:
         """N x (4 + K) float32 rows {x, y, z, tsdf, p_0 .. p_{K-1}}."""
-        return self._gather(self._lib.rsf_gather_valid_classes, 4 + self.num_classes)
+        return self._gather(self._lib.rsf_gather_valid_classes, 4 + self.num_classes, pinned=pinned)
 
     def RayCastMerge(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3, merge_ptr: int, n_planes: int = 3):
         """Sharded grids: raycast with the min-depth merge fused in (rsf_raycast_merge_device).  `merge_ptr` is the
@@ -461,21 +468,32 @@ class TSDFGrid:
         _check(self._lib.rsf_wait(self._h, ticket))
 
     # -- exports --------------------------------------------------------------------------------
-    def _gather(self, fn, ncol, *pre):
+    def _gather(self, fn, ncol, *pre, pinned: bool = False):
         n = C.c_int64(0)
         _check(fn(self._h, *pre, None, 0, C.byref(n)))
-        rows = np.empty((n.value, ncol), np.float32)
+        if pinned:
+            # grid-owned pinned buffer (grown on demand, reused): the DMA lands in it directly, no host copy, no page
+            # faults on a fresh destination.  The returned array is a VIEW, valid until the next pinned gather / close().
+            need = n.value * ncol
+            pa = getattr(self, "_pinned_rows", None)
+            if pa is None or pa.array.size < need:
+                if pa is not None:
+                    pa.free()
+                pa = self._pinned_rows = PinnedArray((max(need + need // 4, 1 << 20),), np.float32)
+            rows = pa.array[:need].reshape(n.value, ncol)
+        else:
+            rows = np.empty((n.value, ncol), np.float32)
         if n.value:
             _check(fn(self._h, *pre, rows.ctypes.data, n.value, C.byref(n)))
         return rows
 
-    def GatherValid(self) -> np.ndarray:
+    def GatherValid(self, pinned: bool = False) -> np.ndarray:
         """N x 4 float32 rows {x,y,z,tsdf} (VoxelSpatialTSDF)."""
-        return self._gather(self._lib.rsf_gather_valid, 4)
+        return self._gather(self._lib.rsf_gather_valid, 4, pinned=pinned)
 
-    def GatherValidSemantic(self) -> np.ndarray:
+    def GatherValidSemantic(self, pinned: bool = False) -> np.ndarray:
         """N x 5 float32 rows {x,y,z,tsdf,prob} (VoxelSpatialTSDFSEGM)."""
-        return self._gather(self._lib.rsf_gather_valid_semantic, 5)
+        return self._gather(self._lib.rsf_gather_valid_semantic, 5, pinned=pinned)
 
     def GatherVoxels(self, volumn: BoundingCube) -> np.ndarray:
         b = volumn.as_array()
@@ -554,6 +572,25 @@ class TSDFGrid:
     def DeleteBlocks(self, block_coords):
         c = np.ascontiguousarray(block_coords, dtype=np.int16).reshape(-1, 3)
         _check(self._lib.rsf_delete_blocks(self._h, c.ctypes.data, len(c)))
+
+    def Resize(self, src, size):
+        """cv::resize(src, Size(W, H)) (INTER_LINEAR) of a torch CUDA tensor -- uint8 HxWx3 / HxW, uint16 or int16 HxW bits,
+        float32 HxW -- on the grid's stream (rsf_resize_device).  size = (H, W).  Returns a new tensor."""
+        import torch
+        assert _is_torch_cuda(src) and src.is_contiguous()
+        ch = src.shape[2] if src.dim() == 3 else 1
+        dst = torch.empty((size[0], size[1]) + ((ch,) if src.dim() == 3 else ()), dtype=src.dtype, device=src.device)
+        _check(self._lib.rsf_resize_device(self._h, src.data_ptr(), src.shape[0], src.shape[1], dst.data_ptr(), size[0], size[1],
+                                           ch, src.element_size()))
+        return dst
+
+    def RebuildTable(self):
+        """Re-insert the alive blocks into an empty table (drops the ghost keys of carved blocks); the library does this
+        by itself when the ghost load passes its threshold."""
+        _check(self._lib.rsf_rebuild_table(self._h))
+
+    def SetTablePolicy(self, max_ghosts: int):
+        _check(self._lib.rsf_set_table_policy(self._h, int(max_ghosts)))
 
     def Retrieve(self, voxel_coords):
         c = np.ascontiguousarray(voxel_coords, dtype=np.int16).reshape(-1, 3)

@@ -92,7 +92,14 @@ struct rsf_grid_s {
   // pinned mirror of the device counters
   Counters* h_ctr = nullptr;
   rsf_frame_stats last{};
+  // table hygiene: the host's (possibly a few frames old) knowledge of the table load, see maybe_rebuild_table
   int64_t table_rebuilds = 0;
+  Counters* h_ctr_snap = nullptr;   // pinned; filled by an asynchronous copy every kSnapEvery frames (no host sync)
+  cudaEvent_t ev_alloc_done = nullptr, ev_snap = nullptr;
+  bool snap_pending = false, snap_stale = false, force_rebuild = false;
+  int64_t known_keys = 0, known_alive = 0;
+  int64_t max_ghosts = 0;           // rebuild threshold (rsf_set_table_policy); 0 = table_slots / 8
+  unsigned frame_no = 0;
   // sharded frame (rsf_shard_frame_device): the presenting rank's planes / flags as mapped into this process
   rsf_shard_link link{};
   bool linked = false;
@@ -102,6 +109,14 @@ struct rsf_grid_s {
   cudaEvent_t ev_step_done[2] = {nullptr, nullptr};   // recorded on `stream` after the step of that frame parity
   unsigned fed = 0, stepped = 0;
   const uint8_t* fed_src[2] = {nullptr, nullptr};     // ingest rank: the caller's packed frame of that parity
+  // export staging (rsf_gather_*): a ring of device chunks and pinned host chunks, allocated on first use and kept
+  static constexpr int kExpRing = 3;
+  static constexpr size_t kExpChunk = (size_t)4 << 20;
+  struct ExpSlot {
+    uint8_t *d = nullptr, *h = nullptr;
+    cudaEvent_t filled = nullptr;   // download kernel done (recorded on stream)
+    cudaEvent_t copied = nullptr;   // D2H done (recorded on s_d2h)
+  } exp_ring[kExpRing];
   // optional per-kernel CUDA-event timing (rsf_profile_*)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[RSF_PROF_NUM];
@@ -148,8 +163,11 @@ int sync_counters(rsf_grid_t g) {
   g->last.culled_blocks = c.culled;
   g->last.table_keys = c.table_keys;
   g->last.table_rebuilds = g->table_rebuilds;
+  g->known_keys = c.table_keys;
+  g->known_alive = g->last.active_blocks;
   if (c.error) {
     const unsigned e = c.error;
+    if (e & kErrTableFull) g->force_rebuild = true;   // the next frame starts from a table without ghosts
     cudaMemsetAsync(&g->view.ctr->error, 0, sizeof(unsigned), g->stream);
     if (e & kErrPoolFull)
       return fail(RSF_ERR_POOL_FULL, "voxel-block pool exhausted (%d blocks); raise rsf_options.pool_blocks",
@@ -182,10 +200,52 @@ struct ProfScope {
   }
 };
 
+// Table hygiene (see rebuild_table_kernel): ghosts = claimed slots whose block has been carved.  The table is rebuilt
+// between two frames when ghosts exceed 1/8 of the slots or the load passes 3/4 -- with slots >= 2 x pool blocks the load
+// therefore never exceeds 1/2 + 1/8 and RSF_ERR_TABLE_FULL cannot become permanent (a frame that did hit it forces a
+// rebuild before the next one).  The decision uses the newest counters the host has WITHOUT synchronising: the blocking
+// entry points refresh them on every call (sync_counters), the asynchronous ones through a 128-byte snapshot copied
+// on the side stream every kSnapEvery frames.
+constexpr unsigned kSnapEvery = 16;
+int rebuild_table_now(rsf_grid_t g) {
+  launch_rebuild_table(g->view, g->table_slots, g->sm_count, g->stream);
+  RSF_CUDA(cudaGetLastError());
+  ++g->table_rebuilds;
+  g->known_keys = g->known_alive;
+  g->force_rebuild = false;
+  if (g->snap_pending) g->snap_stale = true;   // taken before the rebuild: ignore it
+  return RSF_OK;
+}
+int maybe_rebuild_table(rsf_grid_t g) {
+  if (g->snap_pending && cudaEventQuery(g->ev_snap) == cudaSuccess) {
+    g->snap_pending = false;
+    if (!g->snap_stale) {
+      g->known_keys = g->h_ctr_snap->table_keys;
+      g->known_alive = (int64_t)g->view.pool_blocks - g->h_ctr_snap->free_count;
+    }
+    g->snap_stale = false;
+  }
+  const int64_t slots = (int64_t)g->table_slots, ghosts = g->known_keys - g->known_alive;
+  const int64_t limit = g->max_ghosts > 0 ? std::min(g->max_ghosts, slots / 8) : slots / 8;
+  if (g->force_rebuild || ghosts > limit || g->known_keys > slots / 4 * 3) return rebuild_table_now(g);
+  return RSF_OK;
+}
+// after this frame's allocate kernel (the only kernel that claims slots) has been enqueued on g->stream
+int snapshot_counters(rsf_grid_t g) {
+  if (g->snap_pending || (g->frame_no++ % kSnapEvery) != 0) return RSF_OK;
+  RSF_CUDA(cudaEventRecord(g->ev_alloc_done, g->stream));
+  RSF_CUDA(cudaStreamWaitEvent(g->s_side, g->ev_alloc_done, 0));
+  RSF_CUDA(cudaMemcpyAsync(g->h_ctr_snap, g->view.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, g->s_side));
+  RSF_CUDA(cudaEventRecord(g->ev_snap, g->s_side));
+  g->snap_pending = true;
+  return RSF_OK;
+}
+
 // u16 = true: depth / ht / lt point to uint16 images, converted in the allocate kernel with the two scale factors
 int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const void* depth, const void* ht,
                       const void* lt, cudaEvent_t inputs_consumed = nullptr, bool u16 = false, float depth_alpha = 1.f,
                       float prob_alpha = 1.f, const float* class_prob = nullptr) {
+  if (int rc = maybe_rebuild_table(g)) return rc;
   launch_begin_frame(g->view, g->stream);
   // allocate (pixels -> new blocks, appended to the visible list as *fresh*) and select_visible (blocks that were
   // alive before this frame -> visible list) are independent: select skips every slot that is dead or fresh, and a
@@ -210,6 +270,7 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const vo
   // the allocate kernel is the only reader of the raw images (it stages them into d_frame)
   if (inputs_consumed) RSF_CUDA(cudaEventRecord(inputs_consumed, g->stream));
   RSF_CUDA(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
+  if (int rc = snapshot_counters(g)) return rc;
   // K-class extension: the class planes are updated with the weights from BEFORE this frame's TSDF update
   if (class_prob)
     launch_class_update(g->view, f, g->d_frame, class_prob, g->opt.num_classes, g->class_pool, g->sm_count, g->stream);
@@ -218,6 +279,59 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const vo
     launch_integrate(g->view, f, g->d_frame, g->sm_count, g->int_ctas_per_sm, g->stream);
   }
   RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
+}
+
+// Export of `nblk` gathered blocks, `block_bytes` of rows each, to host memory `dst`, in chunks of kExpChunk through a
+// persistent ring (no allocation per call): the download kernel of chunk i + 1 runs on the grid's stream while chunk i
+// crosses PCIe on the read-back stream.  A pinned / registered `dst` receives the DMA directly; a pageable one (the
+// reference's std::vector, a numpy array) is filled by the host from the pinned ring while later chunks are in flight --
+// a cudaMemcpy to pageable memory would stage through the driver's own bounce buffer, serially.
+// fill(blk0, n, d_rows): enqueue the kernel that writes the rows of gathered blocks [blk0, blk0 + n) to d_rows.
+template <class Fill>
+int export_chunked(rsf_grid_t g, int nblk, size_t block_bytes, uint8_t* dst, Fill fill) {
+  if (block_bytes == 0 || block_bytes > rsf_grid_s::kExpChunk) return fail(RSF_ERR_INVALID, "export: %zu-byte blocks do not fit a chunk", block_bytes);
+  for (auto& e : g->exp_ring) {
+    if (!e.d) RSF_CUDA(cudaMalloc((void**)&e.d, rsf_grid_s::kExpChunk));
+    if (!e.h) RSF_CUDA(cudaHostAlloc((void**)&e.h, rsf_grid_s::kExpChunk, cudaHostAllocDefault));
+    if (!e.filled) RSF_CUDA(cudaEventCreateWithFlags(&e.filled, cudaEventDisableTiming));
+    if (!e.copied) RSF_CUDA(cudaEventCreateWithFlags(&e.copied, cudaEventDisableTiming));
+  }
+  cudaPointerAttributes attr{};
+  const bool direct = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();   // (older drivers report an error for plain malloc'ed memory)
+  const int per_chunk = (int)(rsf_grid_s::kExpChunk / block_bytes);
+  const int nchunks = (nblk + per_chunk - 1) / per_chunk;
+  constexpr int R = rsf_grid_s::kExpRing;
+  auto issue = [&](int i) -> int {
+    auto& e = g->exp_ring[i % R];
+    const int b0 = i * per_chunk, n = std::min(per_chunk, nblk - b0);
+    if (i >= R) RSF_CUDA(cudaStreamWaitEvent(g->stream, e.copied, 0));        // the chunk's previous contents have left
+    fill(b0, n, e.d);
+    RSF_CUDA(cudaGetLastError());
+    RSF_CUDA(cudaEventRecord(e.filled, g->stream));
+    RSF_CUDA(cudaStreamWaitEvent(g->s_d2h, e.filled, 0));
+    uint8_t* to = direct ? dst + (size_t)b0 * block_bytes : e.h;
+    RSF_CUDA(cudaMemcpyAsync(to, e.d, (size_t)n * block_bytes, cudaMemcpyDeviceToHost, g->s_d2h));
+    RSF_CUDA(cudaEventRecord(e.copied, g->s_d2h));
+    return RSF_OK;
+  };
+  if (direct) {
+    for (int i = 0; i < nchunks; ++i)
+      if (int rc = issue(i)) return rc;
+    RSF_CUDA(cudaStreamSynchronize(g->s_d2h));
+    return RSF_OK;
+  }
+  for (int i = 0; i < std::min(nchunks, R); ++i)
+    if (int rc = issue(i)) return rc;
+  for (int i = 0; i < nchunks; ++i) {
+    auto& e = g->exp_ring[i % R];
+    const int b0 = i * per_chunk, n = std::min(per_chunk, nblk - b0);
+    RSF_CUDA(cudaEventSynchronize(e.copied));
+    std::memcpy(dst + (size_t)b0 * block_bytes, e.h, (size_t)n * block_bytes);
+    if (i + R < nchunks)
+      if (int rc = issue(i + R)) return rc;
+  }
   return RSF_OK;
 }
 
@@ -242,16 +356,10 @@ int gather_rows(rsf_grid_t g, int mode, const float* bounds, int ncol, float* ro
   if (!rows) return RSF_OK;
   if (cap_rows < *n_rows) return fail(RSF_ERR_CAPACITY, "need %lld rows, capacity %lld", (long long)*n_rows, (long long)cap_rows);
   if (nblk == 0) return RSF_OK;
-  float* d_rows = nullptr;
-  const size_t bytes = (size_t)*n_rows * ncol * sizeof(float);
-  RSF_CUDA(cudaMallocAsync(&d_rows, bytes, g->stream));
-  launch_download_rows(g->view, g->opt.voxel_size, nblk, ncol, d_rows, g->sm_count, g->stream);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(rows, d_rows, bytes, cudaMemcpyDeviceToHost, g->stream);
-  cudaFreeAsync(d_rows, g->stream);
-  if (e != cudaSuccess) return fail(RSF_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
-  RSF_CUDA(cudaStreamSynchronize(g->stream));
-  return RSF_OK;
+  return export_chunked(g, nblk, (size_t)kBlockVol * ncol * sizeof(float), reinterpret_cast<uint8_t*>(rows),
+                        [&](int b0, int n, uint8_t* d) {
+                          launch_download_rows(g->view, g->opt.voxel_size, b0, n, ncol, reinterpret_cast<float*>(d), g->sm_count, g->stream);
+                        });
 }
 
 template <class T>
@@ -380,6 +488,9 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   A((void**)&g->d_ranges, (P / 16 + 4096) * 4 * sizeof(unsigned) + 64);   // tiles <= ceil(W/16) ceil(H/16) <= P/16 + ... for any aspect ratio
   if (o.num_classes > 2) A((void**)&g->class_pool, (size_t)o.pool_blocks * o.num_classes * kBlockVol * sizeof(float));
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&g->h_ctr_snap, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->ev_alloc_done, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->ev_snap, cudaEventDisableTiming) == cudaSuccess;
   if (ok) {
     // key = kEmptyKey (all ones), val = kValFree (-1)
     ok = ok && cudaMemsetAsync(v.table, 0xff, g->table_slots * sizeof(TableEntry), g->stream) == cudaSuccess;
@@ -429,7 +540,16 @@ int rsf_destroy(rsf_grid_t g) {
   if (g->s_side) cudaStreamDestroy(g->s_side);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
+  for (auto& e : g->exp_ring) {
+    if (e.d) cudaFree(e.d);
+    if (e.h) cudaFreeHost(e.h);
+    if (e.filled) cudaEventDestroy(e.filled);
+    if (e.copied) cudaEventDestroy(e.copied);
+  }
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
+  if (g->h_ctr_snap) cudaFreeHost(g->h_ctr_snap);
+  if (g->ev_alloc_done) cudaEventDestroy(g->ev_alloc_done);
+  if (g->ev_snap) cudaEventDestroy(g->ev_snap);
   for (auto& v : g->prof_events)
     for (auto& e : v) {
       cudaEventDestroy(e.first);
@@ -525,13 +645,11 @@ int rsf_gather_valid_classes(rsf_grid_t g, float* rows, int64_t cap_rows, int64_
   if (cap_rows < *n_rows) return fail(RSF_ERR_CAPACITY, "need %lld rows, capacity %lld", (long long)*n_rows, (long long)cap_rows);
   if (nblk == 0) return RSF_OK;
   const int nc = 4 + g->opt.num_classes;
-  DevBuf<float> d_rows(g->stream);
-  RSF_CUDA(d_rows.alloc((size_t)*n_rows * nc));
-  launch_download_class_rows(g->view, g->opt.voxel_size, nblk, g->opt.num_classes, g->class_pool, d_rows.p, g->sm_count, g->stream);
-  RSF_CUDA(cudaGetLastError());
-  RSF_CUDA(cudaMemcpyAsync(rows, d_rows.p, (size_t)*n_rows * nc * sizeof(float), cudaMemcpyDeviceToHost, g->stream));
-  RSF_CUDA(cudaStreamSynchronize(g->stream));
-  return RSF_OK;
+  return export_chunked(g, nblk, (size_t)kBlockVol * nc * sizeof(float), reinterpret_cast<uint8_t*>(rows),
+                        [&](int b0, int n, uint8_t* d) {
+                          launch_download_class_rows(g->view, g->opt.voxel_size, b0, n, g->opt.num_classes, g->class_pool,
+                                                     reinterpret_cast<float*>(d), g->sm_count, g->stream);
+                        });
 }
 
 // cv::Mat::convertTo(CV_32FC1, alpha) multiplies in float: alpha = float(1. / factor)
@@ -578,6 +696,19 @@ int rsf_integrate_u16_device(rsf_grid_t g, const uint8_t* rgb, const uint16_t* d
   if (int rc = make_frame(g, H, W, max_depth, K, pose, &f)) return rc;
   DeviceGuard dg(g->device);
   return enqueue_integrate(g, f, rgb, depth, ht, lt, nullptr, true, u16_alpha(depth_factor), u16_alpha(65535.f));
+}
+
+int rsf_resize_device(rsf_grid_t g, const void* src, int src_H, int src_W, void* dst, int dst_H, int dst_W, int channels,
+                      int elem_bytes) {
+  if (int rc = check_grid(g)) return rc;
+  if (!src || !dst) return fail(RSF_ERR_INVALID, "src / dst must not be NULL");
+  if (src_H <= 0 || src_W <= 0 || dst_H <= 0 || dst_W <= 0 || src_H > 32768 || src_W > 32768 || dst_H > 32768 || dst_W > 32768)
+    return fail(RSF_ERR_INVALID, "image sizes must lie in [1, 32768]");
+  DeviceGuard dg(g->device);
+  if (launch_resize(src, src_H, src_W, dst, dst_H, dst_W, channels, elem_bytes, g->stream) != 0)
+    return fail(RSF_ERR_INVALID, "unsupported format: channels=%d elem_bytes=%d (8UC3, 8UC1, 16UC1, 32FC1)", channels, elem_bytes);
+  RSF_CUDA(cudaGetLastError());
+  return RSF_OK;
 }
 
 int rsf_raycast_device(rsf_grid_t g, float max_depth, int H, int W, const float K[4], const float pose[7], uint8_t* rgba,
@@ -1008,12 +1139,28 @@ int rsf_allocate_blocks(rsf_grid_t g, const int16_t* block_coords, int n) {
   if (int rc = check_grid(g)) return rc;
   if (n < 0 || (n > 0 && !block_coords)) return fail(RSF_ERR_INVALID, "bad block_coords / n");
   DeviceGuard dg(g->device);
+  if (int rc = maybe_rebuild_table(g)) return rc;
   DevBuf<short> dc(g->stream);
   RSF_CUDA(dc.alloc((size_t)n * 3));
   RSF_CUDA(cudaMemcpyAsync(dc.p, block_coords, (size_t)n * 3 * sizeof(short), cudaMemcpyHostToDevice, g->stream));
   launch_allocate_coords(g->view, dc.p, n, g->sm_count, g->stream);
   RSF_CUDA(cudaGetLastError());
   return sync_counters(g);
+}
+
+int rsf_rebuild_table(rsf_grid_t g) {
+  if (int rc = check_grid(g)) return rc;
+  DeviceGuard dg(g->device);
+  if (int rc = sync_counters(g)) return rc;      // known_alive must be exact: it becomes known_keys
+  if (int rc = rebuild_table_now(g)) return rc;
+  return sync_counters(g);
+}
+
+int rsf_set_table_policy(rsf_grid_t g, int64_t max_ghosts) {
+  if (int rc = check_grid(g)) return rc;
+  if (max_ghosts < 0) return fail(RSF_ERR_INVALID, "max_ghosts must be >= 0 (0 = default)");
+  g->max_ghosts = max_ghosts;
+  return RSF_OK;
 }
 
 int rsf_delete_blocks(rsf_grid_t g, const int16_t* block_coords, int n) {

@@ -1,0 +1,116 @@
+"""Table hygiene on long sessions (new in this library; the reference's VoxelHashTable::Delete, voxel_hash.cu:110-159,
+unlinks entries, here carved blocks leave ghost keys that a between-frames rebuild drops): a 2 000-frame walk through
+the multi-room building with a table small enough that the rebuild has to run several times, checked against the
+oracle every frame, and recovery from an exhausted table / pool."""
+import importlib
+
+import numpy as np
+import pytest
+
+import parity
+from oracle_lib import OracleGrid
+
+pytestmark = pytest.mark.gpu
+
+
+def _walk(synth, n_frames, H=96, W=128):
+    """configs[4] building, coarse (3 cm voxels) so that the oracle follows 2 000 frames in about a minute."""
+    seq = synth.config5(n_frames=n_frames, H=H, W=W)
+    seq.voxel_size, seq.truncation, seq.max_depth = 0.03, 0.12, 6.0
+    return seq
+
+
+def _noisy_frame(synth, seq, i):
+    """Frame i with 1 % depth outliers (a depth sensor's flying pixels): every frame allocates a few hundred blocks in
+    free space that later frames carve again -- the ghost-key producer a clean synthetic scene lacks."""
+    rgb, depth, ht, lt = (np.ascontiguousarray(t.cpu().numpy()) for t in
+                          synth.render_torch(seq.scene, seq.K, seq.H, seq.W, seq.poses[i], "cuda"))
+    rng = np.random.default_rng(1000 + i)
+    mask = rng.random(depth.shape) < 0.01
+    depth[mask] *= rng.uniform(0.3, 0.9, size=int(mask.sum())).astype(np.float32)   # in front of the surface: seen through later
+    return rgb, depth, ht, lt
+
+
+def test_long_walk_rebuilds_table_and_keeps_parity(rsf, synth):
+    n = 2000
+    seq = _walk(synth, n)
+    slots_log2, pool, limit = 18, 131072, 1024
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation, pool_blocks=pool, table_slots_log2=slots_log2)
+    g.SetTablePolicy(limit)                                 # default slots / 8: would need a far longer walk
+    o = OracleGrid(seq.voxel_size, seq.truncation, 0)
+    cam = rsf.CameraParams(seq.K, seq.H, seq.W)
+    carved_total = 0
+    for i in range(n):
+        fr = _noisy_frame(synth, seq, i)
+        g.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        o.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+        sg, so = g.stats(), o.stats()
+        for k in ("new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "active_blocks"):
+            assert sg[k] == so[k], (i, k, sg, so)
+        carved_total += sg["carved_blocks"]
+        ghosts = sg["table_keys"] - sg["active_blocks"]
+        assert 0 <= ghosts
+        # bounded: a rebuild runs before the frame after the one that crossed the limit
+        assert ghosts <= limit + sg["new_blocks"] + sg["carved_blocks"] + 64, (i, sg)
+        if i in (499, 1999):
+            r = parity.compare_raycast(g.RayCast(seq.max_depth * 2, cam, seq.poses[i]),
+                                       o.RayCast(seq.max_depth * 2, cam, seq.poses[i]), seq.voxel_size)
+            assert r["hit_mask_mismatch"] == 0 and r["depth_max_vox"] <= 1e-3, (i, r)
+    s = g.stats()
+    assert carved_total > 4 * limit, "the walk must carve enough blocks to need several rebuilds"
+    assert s["table_rebuilds"] >= 4, s
+    m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
+    parity.assert_block_parity(m)
+    assert m["tsdf_bit_mismatch"] == 0 and m["rgb_mismatch"] == 0, m
+    # an explicit rebuild changes nothing observable
+    before = g.ExportBlocks()
+    g.RebuildTable()
+    s2 = g.stats()
+    assert s2["table_keys"] == s2["active_blocks"] == s["active_blocks"] and s2["table_rebuilds"] == s["table_rebuilds"] + 1
+    after = g.ExportBlocks()
+    for a, b in zip(before, after):
+        assert np.array_equal(a, b)
+    # ... including lookups through the rebuilt table (every voxel of 64 random alive blocks + misses)
+    rng = np.random.default_rng(0)
+    blk = before[0][rng.choice(len(before[0]), 64, replace=False)].astype(np.int32)
+    pts = (blk[:, None, :] * 8 + rng.integers(0, 8, size=(64, 16, 3))).reshape(-1, 3).astype(np.int16)
+    r = g.Retrieve(pts)
+    assert r["found"].all()
+    assert not g.Retrieve(np.array([[30000, 30000, 30000]], np.int16))["found"][0]
+
+
+def test_async_path_rebuilds_without_host_sync(rsf, synth):
+    # the pipelined entry points never read the counters back; the load is tracked through the side-stream snapshot
+    seq = _walk(synth, 700)
+    ga = rsf.TSDFGrid(seq.voxel_size, seq.truncation, pool_blocks=32768, table_slots_log2=16)
+    ga.SetTablePolicy(512)
+    gb = rsf.TSDFGrid(seq.voxel_size, seq.truncation, pool_blocks=32768, table_slots_log2=22)   # never needs a rebuild
+    for i in range(700):
+        fr = _noisy_frame(synth, seq, i)
+        # (pageable source buffers: cudaMemcpyAsync has staged them when it returns, they may be dropped right away)
+        ga.IntegrateAsync(*fr, seq.max_depth, seq.K, seq.poses[i])
+        gb.Integrate(*fr, seq.max_depth, seq.K, seq.poses[i])
+    ga.synchronize()
+    sa, sb = ga.stats(), gb.stats()
+    assert sb["table_rebuilds"] == 0
+    assert sa["table_rebuilds"] >= 1, sa
+    assert sa["active_blocks"] == sb["active_blocks"]
+    a, b = ga.ExportBlocks(), gb.ExportBlocks()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_exhausted_table_and_pool_recover(rsf):
+    g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=512, table_slots_log2=10)
+    flood = np.array([[i % 50, (i // 50) % 50, i // 2500] for i in range(3000)], np.int16)   # 3000 distinct > 1024 slots
+    with pytest.raises(rsf.RsfError) as e:
+        g.AllocateBlocks(flood)
+    assert e.value.code in (rsf.RSF_ERR_POOL_FULL, rsf.RSF_ERR_TABLE_FULL)
+    assert g.NumActiveBlock() == 512
+    g.DeleteBlocks(flood)
+    assert g.NumActiveBlock() == 0
+    fresh = np.array([[100 + i, 7, -3] for i in range(300)], np.int16)                          # none of them seen before
+    g.AllocateBlocks(fresh)                                                                   # rebuilt first: all fit
+    s = g.stats()
+    assert s["active_blocks"] == 300 and s["table_keys"] == 300 and s["table_rebuilds"] >= 1, s
+    assert g.Retrieve(fresh * 8)["found"].all()

@@ -153,3 +153,42 @@ def test_folder_dataset_and_dump_formats(tmp_path, synth):
     fmt.write_mesh_bins(str(tmp_path / "mesh"), v, t, p)
     v2, t2, p2 = fmt.read_mesh_bins(str(tmp_path / "mesh"))
     assert np.array_equal(v, v2) and np.array_equal(t, t2) and np.array_equal(p, p2)
+
+
+def test_sens_container_round_trip(tmp_path, synth):
+    """ScanNet .sens (scannet_sens_reader.cc / sensorData.hpp): header, zlib depth, colour, poses."""
+    import importlib
+    fmt = importlib.import_module("ra-slam_b200.formats")
+    seq = synth.config3(n_frames=200)
+    seq.H, seq.W, seq.K = 48, 64, synth.scaled(seq.K, 0.1, 0.1)
+    frames = [seq.frame(i) for i in range(3)]
+    path = str(tmp_path / "scene.sens")
+    # lossless colour at the depth resolution: everything must come back exactly
+    fmt.write_sens(path, seq.K, 1000.0, [(f[0], f[1]) for f in frames], seq.poses[:3], raw_color=True)
+    sr = fmt.SensReader(path)
+    assert len(sr) == 3 and sr.size == (48, 64) and sr.depth_factor == 1000.0 and sr.version == 4
+    assert abs(sr.intrinsics.fx - seq.K.fx) < 1e-4 and abs(sr.intrinsics.cy - seq.K.cy) < 1e-4
+    for i in range(3):
+        rgb, d16, ht, lt = sr.raw(i)
+        assert ht is None and lt is None and d16.dtype == np.uint16
+        assert np.array_equal(rgb, frames[i][0])
+        assert np.array_equal(d16, np.clip(np.rint(frames[i][1].astype(np.float64) * 1000.0), 0, 65535).astype(np.uint16))
+        assert np.allclose(sr.pose(i).matrix(), seq.poses[i].matrix(), atol=2e-6)
+    sr.close()
+    # ScanNet-shaped: JPEG colour stream larger than the depth stream, resized on read like scannet_sens_reader.cc:78
+    fmt.write_sens(path, seq.K, 1000.0, [(f[0], f[1]) for f in frames], seq.poses[:3], color_size=(97, 130))
+    sr = fmt.SensReader(path)
+    assert (sr.color_height, sr.color_width) == (97, 130) and sr.color_compression == fmt.SensReader.COLOR_JPEG
+    import cv2
+    full = sr.color_full(1)
+    assert full.shape == (97, 130, 3)
+    assert np.abs(full.astype(int) - cv2.resize(frames[1][0], (130, 97)).astype(int)).mean() < 12     # JPEG loss only (chroma subsampling on a red / blue checkerboard)
+    rgb = sr.color(1)
+    assert rgb.shape == (48, 64, 3) and np.array_equal(rgb, cv2.resize(full, (64, 48)))
+    called = []
+    sr.color(1, resize=lambda img, size: called.append((img.shape, size)) or img[:size[0], :size[1]])
+    assert called == [((97, 130, 3), (48, 64))]
+    with open(path, "r+b") as f:
+        f.write(b"\x03")
+    with pytest.raises(ValueError):
+        fmt.SensReader(path)

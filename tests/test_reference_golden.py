@@ -18,17 +18,30 @@ import pytest
 import parity
 from oracle_lib import OracleGrid
 
-GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_small.npz")
+GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 TSDF_TOL = 1e-4
 
 
-@pytest.fixture(scope="module")
-def gold():
-    return np.load(GOLDEN)
+# reference_small: config 2 (TUM-shaped, 1 cm voxels, truncation 0.06); reference_config5: BASELINE.json configs[4]'s
+# parameters (5 mm voxels, truncation 0.03, max_depth 8) on a window of the 1296x968 camera in the multi-room building
+@pytest.fixture(scope="module", params=["small", "config5"])
+def gold(request):
+    path = os.path.join(GOLDEN_DIR, f"reference_{request.param}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} has not been generated (tests/golden/make_reference_golden.py {request.param} on a GPU box)")
+    g = dict(np.load(path))
+    g["which"] = request.param
+    return g
 
 
 def _sequence(synth, gold):
-    return synth.config2(n_frames=300, H=int(gold["H"]), W=int(gold["W"]))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(GOLDEN_DIR, "make_reference_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    seq = mod.sequence(gold["which"])
+    assert (seq.H, seq.W) == (int(gold["H"]), int(gold["W"]))
+    return seq
 
 
 def _check(grid, gold, seq, rsf, per_frame_sets=True):
@@ -80,7 +93,8 @@ def _check(grid, gold, seq, rsf, per_frame_sets=True):
 
 def test_oracle_matches_reference_output(gold, synth, rsf):
     """CPU: the oracle restatement against the reference's own output."""
-    _check(OracleGrid(0.01, 0.06, 0), gold, _sequence(synth, gold), rsf)
+    seq = _sequence(synth, gold)
+    _check(OracleGrid(seq.voxel_size, seq.truncation, 0), gold, seq, rsf)
 
 
 @pytest.mark.gpu
