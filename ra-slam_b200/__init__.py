@@ -365,6 +365,16 @@ class TSDFGrid:
         """N x (4 + K) float32 rows {x, y, z, tsdf, p_0 .. p_{K-1}}."""
         return self._gather(self._lib.rsf_gather_valid_classes, 4 + self.num_classes, pinned=pinned)
 
+    def RayCastInternal(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3):
+        """TSDFGrid::RayCast as the reference's callers use it (voxel_tsdf.cu:885-902): render into the grid's own device
+        images (the reference's img_tsdf_rgba_ / img_tsdf_normal_, handed to GLImage8UC4::LoadCuda) -- no read-back.
+        Returns (rgba device address, normal device address, cudaStream_t); asynchronous, `synchronize()` to wait."""
+        K, pose = virtual_cam.intrinsics.as_array(), cam_T_world.as_array()
+        a, b, st = _P(), _P(), _P()
+        _check(self._lib.rsf_raycast_internal_device(self._h, max_depth, virtual_cam.img_h, virtual_cam.img_w, _fptr(K), _fptr(pose),
+                                                     C.byref(a), C.byref(b), C.byref(st)))
+        return a.value, b.value, st.value
+
     def RayCastMerge(self, max_depth: float, virtual_cam: CameraParams, cam_T_world: SE3, merge_ptr: int, n_planes: int = 3):
         """Sharded grids: raycast with the min-depth merge fused in (rsf_raycast_merge_device).  `merge_ptr` is the
         device address of the presenting rank's planes (peer memory on the other ranks)."""

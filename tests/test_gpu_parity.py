@@ -172,7 +172,9 @@ def test_config5_parameters_single_grid_on_a_cropped_frustum(rsf, synth):
     full = synth.config5(n_frames=600, H=968, W=1296)
     H, W = 120, 160
     K = type(full.K)(full.K.fx, full.K.fy, full.K.cx - (1296 - W) / 2, full.K.cy - (968 - H) / 2)
-    seq = synth.Sequence("building-5mm-window", K, H, W, full.poses[::4], full.scene, full.voxel_size, full.truncation, full.max_depth)
+    # the camera dwells for 8 frames at every 4th pose of the walk, so that surfaces reach the raycast's weight threshold
+    poses = [full.poses[i // 8 * 4] for i in range(64)]
+    seq = synth.Sequence("building-5mm-window", K, H, W, poses, full.scene, full.voxel_size, full.truncation, full.max_depth)
     assert (seq.voxel_size, seq.truncation, seq.max_depth) == (0.005, 0.03, 8.0)
     cache = {}
 
@@ -181,14 +183,14 @@ def test_config5_parameters_single_grid_on_a_cropped_frustum(rsf, synth):
             cache[i] = tuple(np.ascontiguousarray(t.cpu().numpy()) for t in synth.render_torch(seq.scene, K, H, W, seq.poses[i], "cuda"))
         return cache[i]
     seq.frame = frame
-    g, o, rays = _run_both(rsf, seq, 32, raycast_at=(15, 31), pool_blocks=1 << 21, table_slots_log2=23)
-    assert g.stats()["active_blocks"] > 2000
+    g, o, rays = _run_both(rsf, seq, 48, raycast_at=(15, 47), pool_blocks=1 << 21, table_slots_log2=23)
+    assert g.stats()["active_blocks"] > 500
     m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
     parity.assert_block_parity(m)
     assert m["tsdf_bit_mismatch"] == 0 and m["rgb_mismatch"] == 0 and m["weight_mismatch"] == 0, m
     for rg, ro in rays:
         r = parity.compare_raycast(rg, ro, seq.voxel_size)
-        assert r["hit_b"] > 0.3 * H * W, r
+        assert r["hit_b"] > 0.2 * H * W, r
         assert r["hit_mask_mismatch"] == 0 and r["depth_max_vox"] <= 1e-3, r
         assert r["rgba_max_abs"] <= 1 and r["normal_max_abs"] <= 1, r
 
