@@ -65,6 +65,7 @@ def parse_args():
                     help="tum = BASELINE.json configs[1] (the headline line); the others are configs[2] / configs[3] shapes")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short 1296x968 ScanNet-shaped measurement")
     ap.add_argument("--no-sharded", action="store_true", help="skip the spatially sharded configs[4] measurement")
+    ap.add_argument("--no-replicas", action="store_true", help="skip the configs[3] (L515 1024x768, one stream per GPU) measurement")
     ap.add_argument("--sharded-height", type=int, default=968)
     ap.add_argument("--sharded-width", type=int, default=1296)
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
@@ -306,9 +307,13 @@ def run_reference(args):
 
 DEPTH = 3                 # frames in flight on the pipelined end-to-end path (the library has 4 staging slots)
 SEC_K, SEC_W = 60, 12     # the short secondary measurement (BASELINE.json's metric also names 1296x968)
+REP_K, REP_W = 40, 10     # the configs[3] replica measurement (L515 1024x768, one stream per GPU)
+# configs/zed_native_l515.yaml:22-27 "extrinsics from l515 to zed"
+L515_EXTRINSICS = [[0.9995, -0.0097, 0.0289, -37.172e-3], [0.009, 0.9997, 0.0247, -22.6717e-3],
+                   [-0.0291, -0.0245, 0.9993, 2.4699e-3], [0, 0, 0, 1]]
 
 
-def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
+def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K, barrier=None, with_classes=True):
     """Short form of the two arms of run_native for a secondary workload: device-resident frames/s (CUDA
     events, L2 flushed between steps) and pipelined end-to-end frames/s with pinned host buffers."""
     H, Wd = seq.H, seq.W
@@ -328,6 +333,8 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
     tot0 = grid.totals()
     grid.profile_enable(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    if barrier:
+        barrier()
     for k in range(K):
         flush.zero_()
         ev[k][0].record()
@@ -362,6 +369,8 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
         grid_e.Integrate(*h_frames[i], seq.max_depth, seq.K, seq.poses[i])
         grid_e.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
     torch.cuda.synchronize()
+    if barrier:
+        barrier()
     t0 = time.perf_counter()
     tickets = []
     for k in range(K):
@@ -394,6 +403,8 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
             grid_u.IntegrateU16(*u_frames[i], seq.depth_factor, seq.max_depth, seq.K, seq.poses[i])
             grid_u.RayCast(rmax, cam, seq.poses[i], outputs=(), out=h_outs[0])
         torch.cuda.synchronize()
+        if barrier:
+            barrier()
         t0 = time.perf_counter()
         tickets = []
         for k in range(K):
@@ -412,6 +423,8 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
     #     resident in HBM; then the export for evaluation (GatherValidSemantic / GatherValidClasses), timed separately
     classes20 = None
     try:
+        if not with_classes:
+            raise StopIteration
         synth = importlib.import_module("ra-slam_b200.synth")
         Kc, Kn, Wn = 20, min(K, 24), min(W, 8)
         grid_c = rsf.TSDFGrid(seq.voxel_size, seq.truncation, device=local_rank, stream=stream.cuda_stream, num_classes=Kc)
@@ -458,6 +471,8 @@ def quick_native(rsf, torch, dev, local_rank, seq, frames, W, K):
                      "export_gather_valid_classes": export_entry(grid_c.GatherValidClasses)}
         grid_c.close()
         del c_frames
+    except StopIteration:
+        classes20 = None
     except Exception as e:      # the extension must never take the headline measurement down with it
         classes20 = {"error": repr(e)}
     P = H * Wd
@@ -646,6 +661,43 @@ def run_native(args):
                                         W=args.sharded_width)
         except Exception as e:      # never take the headline line down
             sharded = {"error": repr(e)}
+    # ---------------- configs[3] as written: one independent L515 stream per GPU (weak scaling) ----------------
+    # 1024x768, the L515 intrinsics, depthmap_factor 4000, every pose composed with the camera extrinsics on the host
+    # (configs/zed_native_l515.yaml:22-34, modules/tsdf_module.cc:29), seeds 10 + rank; all ranks run at the same time.
+    replicas4 = None
+    if not args.no_replicas:
+        try:
+            synth = importlib.import_module("ra-slam_b200.synth")
+            s4 = synth.config4(seed=10 + rank, n_frames=REP_W + REP_K, hires=True)
+            E = rsf.SE3.from_matrix(np.array(L515_EXTRINSICS, np.float32))
+            s4.poses = [rsf.SE3(E.q, E.t) * p for p in s4.poses]
+            f4 = [tuple(np.ascontiguousarray(t.cpu().numpy()) for t in
+                        synth.render_torch(s4.scene, s4.K, s4.H, s4.W, s4.poses[i], dev, depth_factor=s4.depth_factor))
+                  for i in range(REP_W + REP_K)]
+            r4 = quick_native(rsf, torch, dev, local_rank, s4, f4, REP_W, REP_K, barrier=barrier, with_classes=False)
+            P4 = s4.H * s4.W
+            mine = torch.tensor([r4["value"], r4["e2e"]["value"], (r4["e2e_u16_inputs"] or {}).get("value", 0.0)],
+                                dtype=torch.float64, device=dev)
+            allr = [mine]
+            if dist is not None:
+                allr = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allr, mine)
+            rows = [[float(x) for x in t.tolist()] for t in allr]
+            slow = [min(r[j] for r in rows) for j in range(3)]
+            replicas4 = {"workload": "configs[3] L515-shaped 1024x768, extrinsics composed per pose, one independent sequence per GPU "
+                                     "(seeds 10..), integrate+raycast per frame", "steps": REP_K, "warmup": REP_W, "unit": UNIT,
+                         "scaling": "weak", "n_gpus": world,
+                         "value": world * slow[0], "e2e": {"value": world * slow[1], "unit": UNIT, "h2d_bytes_per_step": 15 * P4,
+                                                          "d2h_bytes_per_step": 12 * P4,
+                                                          "pcie_gbs_per_rank": {"h2d": slow[1] * 15 * P4 / 1e9, "d2h": slow[1] * 12 * P4 / 1e9}},
+                         "e2e_u16_inputs": {"value": world * slow[2], "unit": UNIT, "h2d_bytes_per_step": 9 * P4,
+                                            "d2h_bytes_per_step": 12 * P4,
+                                            "pcie_gbs_per_rank": {"h2d": slow[2] * 9 * P4 / 1e9, "d2h": slow[2] * 12 * P4 / 1e9}},
+                         "per_rank_fps": {"columns": ["value", "e2e", "e2e_u16_inputs"], "rows": rows},
+                         "note": "aggregate = n_gpus x the slowest rank's frames/s (ranks start together behind a barrier)"}
+            del f4
+        except Exception as e:      # never take the headline line down
+            replicas4 = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -698,6 +750,7 @@ def run_native(args):
         "map": {"active_blocks": stats_end["active_blocks"], "high_water": stats_end["high_water"]},
     }
     line["sharded_config5"] = sharded
+    line["replicas_config4"] = replicas4
     if world == 1 and args.workload == "tum" and not args.no_secondary:
         synth = importlib.import_module("ra-slam_b200.synth")
         s2 = synth.config3(n_frames=200, hires=True)

@@ -959,43 +959,22 @@ int rsf_raycast_async(rsf_grid_t g, float max_depth, int H, int W, const float K
   const int slot = (int)(g->out_next++ % rsf_grid_s::kSlots);
   auto& sl = g->out[slot];
   RSF_CUDA(cudaStreamWaitEvent(g->stream, sl.done, 0));       // read-back of the previous user has finished
-  // Two row bands: the D2H copy of the upper half of the images runs while the lower half is still being marched (the
-  // reference renders, then copies, voxel_tsdf.cu:885-902).  Small images are not worth a second launch.
-  const int prow = (H + 3) / 4;
-  const int rows0 = H >= 256 ? (prow / 2) : prow;              // patch rows (4 pixel rows each) of the first band
+  // (Rendering in two row bands so that the read-back of the first overlaps the march of the second was measured and
+  // dropped: the kernel is bound by its longest patch, two launches have two tails, and the five extra API calls per frame
+  // cost the pipelined path 15 % -- 5 950 instead of 6 950 frames/s -- without helping the blocking one.)
   const size_t P = (size_t)H * W;
-  const float step = g->opt.truncation / 2;                   // step_size = truncation / 2, voxel_tsdf.cu:892
-  uchar4* d_rgba = rgba ? sl.rgba : nullptr;
-  uchar4* d_normal = normal ? sl.normal : nullptr;
-  float* d_depth = depth ? sl.depth : nullptr;
-  float* d_prob = prob ? sl.prob : nullptr;
   {
     ProfScope p(g, RSF_PROF_RAYCAST);
-    launch_raycast_prepass(g->view, f, step, g->d_ranges, g->sm_count, g->stream);
-    launch_raycast_band(g->view, f, step, g->d_ranges, d_rgba, d_normal, d_depth, d_prob, g->sm_count, g->stream, 0, rows0, 0);
+    launch_raycast(g->view, f, g->opt.truncation / 2, g->d_ranges, rgba ? sl.rgba : nullptr, normal ? sl.normal : nullptr,
+                   depth ? sl.depth : nullptr, prob ? sl.prob : nullptr, g->sm_count, g->stream);   // step_size = truncation / 2, voxel_tsdf.cu:892
   }
   RSF_CUDA(cudaGetLastError());
-  auto read_back = [&](size_t px0, size_t npx) -> int {
-    if (rgba) RSF_CUDA(cudaMemcpyAsync(rgba + px0 * 4, sl.rgba + px0, npx * 4, cudaMemcpyDeviceToHost, g->s_d2h));
-    if (normal) RSF_CUDA(cudaMemcpyAsync(normal + px0 * 4, sl.normal + px0, npx * 4, cudaMemcpyDeviceToHost, g->s_d2h));
-    if (depth) RSF_CUDA(cudaMemcpyAsync(depth + px0, sl.depth + px0, npx * sizeof(float), cudaMemcpyDeviceToHost, g->s_d2h));
-    if (prob) RSF_CUDA(cudaMemcpyAsync(prob + px0, sl.prob + px0, npx * sizeof(float), cudaMemcpyDeviceToHost, g->s_d2h));
-    return RSF_OK;
-  };
-  const size_t px_band0 = std::min(P, (size_t)rows0 * 4 * W);
   RSF_CUDA(cudaEventRecord(sl.ready, g->stream));
   RSF_CUDA(cudaStreamWaitEvent(g->s_d2h, sl.ready, 0));
-  if (int rc = read_back(0, px_band0)) return rc;
-  if (rows0 < prow) {
-    {
-      ProfScope p(g, RSF_PROF_RAYCAST);
-      launch_raycast_band(g->view, f, step, g->d_ranges, d_rgba, d_normal, d_depth, d_prob, g->sm_count, g->stream, rows0, prow - rows0, 1);
-    }
-    RSF_CUDA(cudaGetLastError());
-    RSF_CUDA(cudaEventRecord(sl.ready, g->stream));
-    RSF_CUDA(cudaStreamWaitEvent(g->s_d2h, sl.ready, 0));
-    if (int rc = read_back(px_band0, P - px_band0)) return rc;
-  }
+  if (rgba) RSF_CUDA(cudaMemcpyAsync(rgba, sl.rgba, P * 4, cudaMemcpyDeviceToHost, g->s_d2h));
+  if (normal) RSF_CUDA(cudaMemcpyAsync(normal, sl.normal, P * 4, cudaMemcpyDeviceToHost, g->s_d2h));
+  if (depth) RSF_CUDA(cudaMemcpyAsync(depth, sl.depth, P * sizeof(float), cudaMemcpyDeviceToHost, g->s_d2h));
+  if (prob) RSF_CUDA(cudaMemcpyAsync(prob, sl.prob, P * sizeof(float), cudaMemcpyDeviceToHost, g->s_d2h));
   RSF_CUDA(cudaEventRecord(sl.done, g->s_d2h));
   if (ticket) *ticket = slot;
   return RSF_OK;

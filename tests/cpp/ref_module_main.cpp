@@ -54,6 +54,7 @@ int main(int argc, char** argv) {
   const auto q = sys.Query(BoundingCube<float>{0.f, 2.5f, 0.f, 4.f, 0.f, 1.5f});
   std::ofstream(out + ".query", std::ios::binary).write((const char*)q.data(), (std::streamsize)(q.size() * sizeof(VoxelSpatialTSDF)));
   std::printf("query_rows %zu loads %d %d\n", q.size(), rgba.loads, normal.loads);
-  sys.terminate();
+  // (no sys.terminate() here: the reference's destructor calls it, modules/tsdf_module.cc:20, and its terminate() joins
+  // the worker unconditionally, :127-133 -- a second call throws std::system_error)
   return 0;
 }

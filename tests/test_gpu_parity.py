@@ -195,6 +195,39 @@ def test_config5_parameters_single_grid_on_a_cropped_frustum(rsf, synth):
         assert r["rgba_max_abs"] <= 1 and r["normal_max_abs"] <= 1, r
 
 
+@pytest.mark.parametrize("shift,world", [(2, 4), (5, 8), (0, 3)])
+def test_sharded_grids_match_the_sharded_oracle(rsf, synth, shift, world):
+    """Every rank's grid of a spatially sharded scene (ownership-first allocate, whole-patch skip when none of a patch's
+    samples can fall into a wanted block) against the oracle restricted to the same shard: per-frame counters and the
+    final block contents must be identical, and the owned sets must partition the single grid's block set."""
+    seq = synth.config5(n_frames=200, H=120, W=160) if shift == 5 else synth.config2(n_frames=300, H=120, W=160)
+    n = 14
+    frames = [seq.frame(i) for i in range(n)]
+    whole = rsf.TSDFGrid(seq.voxel_size, seq.truncation, pool_blocks=1 << 17, table_slots_log2=19)
+    for i in range(n):
+        whole.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
+    owned = []
+    for r in range(world):
+        g = rsf.TSDFGrid(seq.voxel_size, seq.truncation, pool_blocks=1 << 17, table_slots_log2=19, shard_rank=r, shard_world=world,
+                         shard_shift=shift, shard_halo=1)
+        o = OracleGrid(seq.voxel_size, seq.truncation, 0)
+        o.set_shard(r, world, shift, 1)
+        for i in range(n):
+            g.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
+            o.Integrate(*frames[i], seq.max_depth, seq.K, seq.poses[i])
+            sg, so = g.stats(), o.stats()
+            for k in ("new_blocks", "visible_blocks", "updated_voxels", "carved_blocks", "active_blocks"):
+                assert sg[k] == so[k], (r, i, k, sg, so)
+        m = parity.compare_blocks(g.ExportBlocks(), o.ExportBlocks())
+        parity.assert_block_parity(m)
+        assert m["tsdf_bit_mismatch"] == 0 and m["rgb_mismatch"] == 0, (r, m)
+        owned.append(parity.keys_of(g.ExportBlockCoords(owned_only=True)))
+        g.close()
+    union = np.concatenate(owned)
+    assert len(np.unique(union)) == len(union)                                       # no block has two owners
+    assert np.array_equal(np.sort(union), np.sort(parity.keys_of(whole.ExportBlocks()[0])))
+
+
 def test_sharded_product_path_two_ranks_nccl(rsf, tmp_path):
     """The product's sharded flow (ShardedScene: copy-engine frame tree, rsf_shard_step_device, fused min-depth merge over
     NVLink peer memory) on two real ranks, NCCL process group, configs[4] scene at 640x480: the union of the owned block

@@ -88,11 +88,23 @@ def _tie_explained(seq, n, coords, vox):
     return hit
 
 
-def _check_volume(rsf, ref, seq, n, raycast_at):
+def _check_volume(rsf, ref, seq, n, raycast_at, late_blocks_ok=0.0):
+    """late_blocks_ok: fraction of the final block set the reference may still be missing.  Its try-lock insert drops
+    contended requests and retries them a frame later (utils/tsdf/voxel_hash.cu:71-75,93-104), so whether the LAST frame's
+    requests all went through is a matter of thread timing; the low-resolution sequences end with identical sets, at
+    ~1 M pixels per frame a handful of blocks is still in flight."""
     g, r, dirty, born_clean, rays = _history(rsf, ref, seq, n, raycast_at)
     eg, er = g.ExportBlocks(), r.ExportBlocks()
     kg, kr = parity.keys_of(eg[0]), parity.keys_of(er[0])
-    assert np.array_equal(kg, kr), "final allocated block-coordinate sets differ"          # identical sets
+    if late_blocks_ok == 0.0:
+        assert np.array_equal(kg, kr), "final allocated block-coordinate sets differ"          # identical sets
+    else:
+        assert np.isin(kr, kg).all(), "the reference holds blocks the product lacks"
+        assert len(kg) - len(kr) <= late_blocks_ok * len(kg), (len(kg), len(kr))
+        both = np.isin(kg, kr)                                                                # (both exports are sorted by key)
+        eg = tuple(a[both] for a in eg)
+        kg = kg[both]
+        assert np.array_equal(kg, kr)
     keep = ~np.isin(kg, np.array(sorted(dirty), dtype=np.uint64))
     assert keep.mean() > 0.94          # the reference drops a thread-timing-dependent 1-2 % of first-frame inserts
     ta, tb = eg[1][keep], er[1][keep]
@@ -116,7 +128,14 @@ def _check_volume(rsf, ref, seq, n, raycast_at):
     # colour: strict (+-1) on blocks alive since before the first carve and never re-allocated (no recycled pool slot)
     strict = np.isin(kg[keep], np.array(sorted(born_clean), dtype=np.uint64))[:, None] & good & ((wa > 1) | (ta != -1))
     off = (np.abs(ca - cb).max(axis=-1) > 1) & strict
-    assert off.sum() <= 1e-3 * max(strict.sum(), 1), f"{off.sum()} of {strict.sum()} voxels differ in colour by > 1"
+    if off.sum() > 1e-3 * max(strict.sum(), 1):
+        # A voxel that picked the neighbouring pixel at a rounding tie blends that pixel's COLOUR, which on a textured
+        # surface differs by far more than its depth does: at ~1 M pixels per frame the colour outliers outnumber the TSDF
+        # ones.  They must still be rare, and (nearly) every one of them must be such a tie.
+        assert off.sum() <= 3e-3 * strict.sum(), f"{off.sum()} of {strict.sum()} voxels differ in colour by > 1"
+        bi, vi = np.nonzero(off)
+        expl = _tie_explained(seq, n, eg[0][keep][bi], vi)
+        assert (~expl).sum() <= 0.05 * len(bi), f"{(~expl).sum()} of {len(bi)} colour outliers are not rounding ties"
     # raycast: same hit mask up to a few tie pixels; colours equal on nearly all hit pixels
     for a, b in rays:
         ha, hb = a["rgba"][..., 3] > 0, b["rgba"][..., 3] > 0
@@ -178,13 +197,29 @@ def _same_positions(a, b):
     return a, b
 
 
+def _common_rows(a, b, voxel_size, missing_ok):
+    """Rows of the two exports that describe the same voxel (the reference may still be missing `missing_ok` of them, see
+    _check_volume); positions of the common rows must be bit-identical."""
+    def key(rows):
+        v = np.rint(rows[:, :3].astype(np.float64) / voxel_size).astype(np.int64) + 32768
+        return v[:, 0] | (v[:, 1] << 16) | (v[:, 2] << 32)
+    ka, kb = key(a), key(b)
+    assert len(np.unique(ka)) == len(ka) and len(np.unique(kb)) == len(kb)
+    _, ia, ib = np.intersect1d(ka, kb, return_indices=True)
+    assert len(ib) == len(kb), "the reference exported voxels the product did not"
+    assert len(ka) - len(ia) <= missing_ok * len(ka), (len(ka), len(kb))
+    a, b = a[ia], b[ib]
+    assert np.array_equal(a[:, :3].view(np.uint32), b[:, :3].view(np.uint32))
+    return a, b
+
+
 def test_reference_config3_scannet_1296x968(rsf, ref, synth):
     # BASELINE.json configs[2] at the resolution the metric is also quoted on (and bench.py measures): 1296 x 968
     seq = _gpu_rendered(synth, synth.config3(n_frames=60, hires=True))
-    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(19,))
+    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(19,), late_blocks_ok=2e-3)
     a, b = g.GatherValidSemantic(), r.GatherValidSemantic()             # utils/tsdf/voxel_tsdf.cu:504-530
-    assert a.shape == b.shape and a.shape[1] == 5 and len(a) > 1_000_000
-    a, b = _same_positions(a, b)
+    assert a.shape[1] == 5 and b.shape[1] == 5 and len(a) > 1_000_000
+    a, b = _common_rows(a, b, seq.voxel_size, 2e-3)
     assert (np.abs(a[:, 3] - b[:, 3]) > TSDF_TOL).mean() < 1e-2
     assert (np.abs(a[:, 4] - b[:, 4]) > 1e-4).mean() < 1e-2
     # the pinned-destination export returns the same rows as the pageable one
@@ -208,8 +243,8 @@ def test_reference_config4_l515_1024x768_extrinsics(rsf, ref, synth):
     assert abs(float(np.linalg.norm(E.q.astype(np.float64))) - 1.0) > 1e-6   # the point of the test: a non-unit quaternion
     seq.poses = [rsf.SE3(E.q, E.t) * p for p in seq.poses]
     seq = _gpu_rendered(synth, seq)
-    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(9, 19))
-    a, b = _same_positions(g.GatherValid(), r.GatherValid())
+    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(9, 19), late_blocks_ok=2e-3)
+    a, b = _common_rows(g.GatherValid(), r.GatherValid(), seq.voxel_size, 2e-3)
     assert (np.abs(a[:, 3] - b[:, 3]) > TSDF_TOL).mean() < 1e-2
 
 

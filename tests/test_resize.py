@@ -95,4 +95,4 @@ def test_resized_frame_integrates_like_the_cpu_prepared_one(rsf, synth):
     a, b = ga.ExportBlocks(), gb.ExportBlocks()
     assert len(a[0]) > 500
     for x, y in zip(a, b):
-        assert np.array_equal(x, y)
+        assert np.array_equal(x, y, equal_nan=x.dtype.kind == "f")     # (no segmentation: ht = 0 -> probabilities 0 or NaN)
