@@ -741,6 +741,14 @@ def run_native(args):
         "gpu_launches": int(sum(v[1] for v in prof.values()) + int_n + prof["raycast"][1]),
         "roofline": {"kernel": "integrate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "traffic_source": "profiles/integrate_traffic.json: DRAM bytes of ONE launch captured with ncu --set full in a separate run "
+                                       "(2326 visible blocks, 22.09 MB algorithmic in that launch), not measured during this run",
+                     # the kernel is bound by instruction issue before it is bound by HBM (profiles/r2_ncu_summary.md E):
+                     # ~223 warp instructions per voxel (IEEE operations in the reference's order) against 24 algorithmic bytes
+                     "issue_bound": {"warp_instructions_per_voxel": 223, "warp_instructions_per_visible_block": 894 * 4,
+                                     "issue_peak_ginstr_s": 148 * 4 * 1.965,
+                                     "floor_us_per_launch": 894 * 4 * (vis / max(int_n, 1)) / (148 * 4 * 1.965e3),
+                                     "source": "ncu source view of the captured launch (8.36 M warp instructions / 2336 blocks)"},
                      "algorithmic_bytes_per_launch": alg_bytes / max(int_n, 1),
                      "updated_voxels_per_launch": upd / max(int_n, 1), "visible_blocks_per_launch": vis / max(int_n, 1),
                      "voxel_updates_per_s": upd / (int_ms * 1e-3) if int_ms else None},
