@@ -149,8 +149,10 @@ int make_frame(rsf_grid_t g, int H, int W, float max_depth, const float* K, cons
   return RSF_OK;
 }
 
-// read the counters back (blocking) and translate sticky device errors
-int sync_counters(rsf_grid_t g) {
+// Read the counters back (blocking).  report = true (the integrate / allocate / synchronize entry points): translate and
+// clear the sticky device error bits.  report = false (exports, statistics): leave them for the next reporting call -- a
+// gather that succeeded must not fail because an earlier frame overflowed the pool.
+int sync_counters(rsf_grid_t g, bool report = true) {
   RSF_CUDA(cudaMemcpyAsync(g->h_ctr, g->view.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, g->stream));
   RSF_CUDA(cudaStreamSynchronize(g->stream));
   const Counters& c = *g->h_ctr;
@@ -165,9 +167,9 @@ int sync_counters(rsf_grid_t g) {
   g->last.table_rebuilds = g->table_rebuilds;
   g->known_keys = c.table_keys;
   g->known_alive = g->last.active_blocks;
-  if (c.error) {
+  if (c.error && (c.error & kErrTableFull)) g->force_rebuild = true;   // the next frame starts from a table without ghosts
+  if (c.error && report) {
     const unsigned e = c.error;
-    if (e & kErrTableFull) g->force_rebuild = true;   // the next frame starts from a table without ghosts
     cudaMemsetAsync(&g->view.ctr->error, 0, sizeof(unsigned), g->stream);
     if (e & kErrPoolFull)
       return fail(RSF_ERR_POOL_FULL, "voxel-block pool exhausted (%d blocks); raise rsf_options.pool_blocks",
@@ -350,7 +352,7 @@ int gather_rows(rsf_grid_t g, int mode, const float* bounds, int ncol, float* ro
   RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
   launch_gather_select(g->view, mode, g->opt.shard_world > 1, lo, hi, g->sm_count, g->stream);
   RSF_CUDA(cudaGetLastError());
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   const int nblk = g->h_ctr->gather_count;
   *n_rows = (int64_t)nblk * kBlockVol;
   if (!rows) return RSF_OK;
@@ -638,7 +640,7 @@ int rsf_gather_valid_classes(rsf_grid_t g, float* rows, int64_t cap_rows, int64_
   RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
   launch_gather_select(g->view, 0, g->opt.shard_world > 1, S3{0, 0, 0}, S3{0, 0, 0}, g->sm_count, g->stream);
   RSF_CUDA(cudaGetLastError());
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   const int nblk = g->h_ctr->gather_count;
   *n_rows = (int64_t)nblk * kBlockVol;
   if (!rows) return RSF_OK;
@@ -1008,7 +1010,7 @@ int rsf_num_active_blocks(rsf_grid_t g, int64_t* n) {
   if (int rc = check_grid(g)) return rc;
   if (!n) return fail(RSF_ERR_INVALID, "n must not be NULL");
   DeviceGuard dg(g->device);
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   *n = g->last.active_blocks;
   return RSF_OK;
 }
@@ -1017,7 +1019,7 @@ int rsf_get_stats(rsf_grid_t g, rsf_frame_stats* s) {
   if (int rc = check_grid(g)) return rc;
   if (!s) return fail(RSF_ERR_INVALID, "stats must not be NULL");
   DeviceGuard dg(g->device);
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   *s = g->last;
   return RSF_OK;
 }
@@ -1040,7 +1042,7 @@ int rsf_gather_valid_mesh(rsf_grid_t g, float* vertices, int64_t cap_vertices, i
   RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
   launch_gather_select(g->view, 0, g->opt.shard_world > 1, S3{0, 0, 0}, S3{0, 0, 0}, g->sm_count, g->stream);
   RSF_CUDA(cudaGetLastError());
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   const int nblk = g->h_ctr->gather_count;
   DevBuf<int2> counts(g->stream), offsets(g->stream);
   DevBuf<long long> totals(g->stream);
@@ -1084,7 +1086,7 @@ int rsf_export_blocks(rsf_grid_t g, int owned_only, int16_t* coords, float* tsdf
   RSF_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(g->view.ctr) + kCtrGatherOff, 0, sizeof(int), g->stream));
   launch_gather_select(g->view, 0, owned_only, S3{0, 0, 0}, S3{0, 0, 0}, g->sm_count, g->stream);
   RSF_CUDA(cudaGetLastError());
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   const int nblk = g->h_ctr->gather_count;
   *n_blocks = nblk;
   if (!coords && !tsdf && !rgbw && !prob) return RSF_OK;
@@ -1257,7 +1259,7 @@ int rsf_get_totals(rsf_grid_t g, int64_t totals[5]) {
   if (int rc = check_grid(g)) return rc;
   if (!totals) return fail(RSF_ERR_INVALID, "totals must not be NULL");
   DeviceGuard dg(g->device);
-  if (int rc = sync_counters(g)) return rc;
+  if (int rc = sync_counters(g, false)) return rc;
   const Counters& c = *g->h_ctr;   // totals exclude the frame still held in the per-frame counters
   totals[0] = (int64_t)c.tot_frames;
   totals[1] = (int64_t)(c.tot_new_blocks + c.new_blocks);

@@ -78,6 +78,21 @@ def test_pool_exhaustion_is_an_error_not_ub(rsf):
     assert g.NumActiveBlock() == 64
 
 
+def test_sticky_error_is_reported_by_integrate_and_synchronize_only(rsf, synth):
+    # a frame that overflows the pool on the pipelined path: exports and statistics keep working (the overflow is not
+    # THEIR failure), the next synchronize reports it once, then the grid is clean again
+    seq = synth.config1(n_frames=100, H=120, W=160)
+    g = rsf.TSDFGrid(seq.voxel_size, seq.truncation, pool_blocks=64, table_slots_log2=10)
+    fr = tuple(np.ascontiguousarray(a) for a in seq.frame(0))
+    g.IntegrateAsync(*fr, seq.max_depth, seq.K, seq.poses[0])
+    rows = g.GatherValid()
+    assert len(rows) == 64 * 512 and g.NumActiveBlock() == 64 and g.stats()["active_blocks"] == 64
+    with pytest.raises(rsf.RsfError) as e:
+        g.synchronize()
+    assert e.value.code == rsf.RSF_ERR_POOL_FULL
+    g.synchronize()                                             # reported once
+
+
 def test_trilinear_matches_oracle(rsf):
     g = rsf.TSDFGrid(0.01, 0.06, pool_blocks=4096, table_slots_log2=14)
     o = OracleGrid(0.01, 0.06, 1)
