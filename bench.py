@@ -536,8 +536,11 @@ def run_native(args):
     tot0 = grid.totals()
     grid.profile_enable(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # clocks are sampled for rank 0's GPU only: the JSON line carries one `clocks` object, and eight nvidia-smi pollers (each
+    # query takes driver-wide locks) perturb the launch latency of every rank
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     barrier()
     t_wall0 = time.time()
     for k in range(K):
@@ -644,7 +647,7 @@ def run_native(args):
     grid_r.close()
     barrier()
     t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
     # ---------------- max over ranks ---------------------------------------------------------------
     if dist is not None:
