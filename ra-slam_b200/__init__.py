@@ -58,7 +58,7 @@ class rsf_frame_stats(C.Structure):
 
 # every symbol include/rsfusion.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
-_F4 = C.POINTER(C.c_float)
+_F4 = C.c_void_p   # const float* arguments (K[4], pose[7], bounds[6]): passed as plain addresses, see _fptr
 ABI = {
     "rsf_default_options": (None, [C.POINTER(rsf_options)]),
     "rsf_abi_version": (C.c_int, []),
@@ -244,11 +244,16 @@ class SE3:
 
     def as_array(self) -> np.ndarray:
         """{qw,qx,qy,qz,tx,ty,tz} -- the `pose` argument of the C ABI."""
-        return np.concatenate([self.q, self.t]).astype(np.float32)
+        a = np.empty(7, np.float32)
+        a[:4] = self.q
+        a[4:] = self.t
+        return a
 
 
 def _fptr(a: np.ndarray):
-    return a.ctypes.data_as(_F4)
+    """Address of a contiguous float32 array (the caller keeps `a` alive across the call).  `ndarray.ctypes.data_as(POINTER)`
+    costs ~5 us per argument -- a quarter of the host time of a 150 us frame -- the raw address 0.3 us."""
+    return a.__array_interface__["data"][0]
 
 
 def _is_torch_cuda(x) -> bool:
