@@ -192,3 +192,26 @@ def test_sens_container_round_trip(tmp_path, synth):
         f.write(b"\x03")
     with pytest.raises(ValueError):
         fmt.SensReader(path)
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` without a GPU times the CPU port and prints one JSON line with the contract's keys; the
+    native arm refuses to run without a GPU (no CPU fallback)."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3",
+                          "--height", "120", "--width", "160", "--no-secondary"], capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-1000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+    nat = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "3", "--no-secondary", "--no-sharded",
+                          "--no-replicas", "--no-cpu-baseline"], capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    assert nat.returncode != 0 and "no CPU fallback" in (nat.stderr + nat.stdout)
