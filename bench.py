@@ -755,8 +755,9 @@ def run_native(args):
                                                "TSDFGrid::RayCast(GLImage8UC4*, GLImage8UC4*): host images in, render into the grid's device "
                                                "images, no read-back -- byte for byte what `--impl reference` times",
                 "checksum": checksum},
-        # per frame: begin_frame, allocate, select_visible, integrate, tile_range, raycast
-        "gpu_launches": int(sum(v[1] for v in prof.values()) + int_n + prof["raycast"][1]),
+        # per frame: begin_frame, allocate, depth_tiles, select_visible, integrate, tile_range, raycast (7 kernels of this library;
+        # the per-kernel event pairs count allocate / select / integrate / raycast once each)
+        "gpu_launches": int(sum(v[1] for v in prof.values()) + int_n + prof["select"][1] + prof["raycast"][1]),
         "roofline": {"kernel": "integrate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "traffic_source": "profiles/integrate_traffic.json: DRAM bytes of ONE launch captured with ncu --set full in a separate run "
