@@ -96,6 +96,7 @@ struct rsf_grid_s {
   int64_t table_rebuilds = 0;
   Counters* h_ctr_snap = nullptr;   // pinned; filled by an asynchronous copy every kSnapEvery frames (no host sync)
   cudaEvent_t ev_alloc_done = nullptr, ev_snap = nullptr;
+  cudaEvent_t ev_prepass_go = nullptr, ev_prepass = nullptr;   // fused frame: raycast pre-pass on the side stream, next to integrate
   bool snap_pending = false, snap_stale = false, force_rebuild = false;
   int64_t known_keys = 0, known_alive = 0;
   int64_t max_ghosts = 0;           // rebuild threshold (rsf_set_table_policy); 0 = table_slots / 8
@@ -246,7 +247,7 @@ int snapshot_counters(rsf_grid_t g) {
 // u16 = true: depth / ht / lt point to uint16 images, converted in the allocate kernel with the two scale factors
 int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const void* depth, const void* ht,
                       const void* lt, cudaEvent_t inputs_consumed = nullptr, bool u16 = false, float depth_alpha = 1.f,
-                      float prob_alpha = 1.f, const float* class_prob = nullptr) {
+                      float prob_alpha = 1.f, const float* class_prob = nullptr, const Frame* prepass_for = nullptr) {
   if (int rc = maybe_rebuild_table(g)) return rc;
   launch_begin_frame(g->view, g->stream);
   // allocate (pixels -> new blocks, appended to the visible list as *fresh*) and select_visible (blocks that were
@@ -271,6 +272,16 @@ int enqueue_integrate(rsf_grid_t g, const Frame& f, const uint8_t* rgb, const vo
   }
   // the allocate kernel is the only reader of the raw images (it stages them into d_frame)
   if (inputs_consumed) RSF_CUDA(cudaEventRecord(inputs_consumed, g->stream));
+  if (prepass_for) {
+    // Fused frame (rsf_shard_frame_device): the raycast's pre-pass for the view `prepass_for` runs on the side stream
+    // next to the integrate kernel instead of after it.  It needs the blocks allocate has just added; the blocks
+    // integrate is about to carve may or may not still be in the list it walks -- either way the per-tile ranges only
+    // get wider (a carved block is a miss for the march), so the rendered image is unchanged.
+    RSF_CUDA(cudaEventRecord(g->ev_prepass_go, g->stream));
+    RSF_CUDA(cudaStreamWaitEvent(g->s_side, g->ev_prepass_go, 0));
+    launch_raycast_prepass(g->view, *prepass_for, g->opt.truncation / 2, g->d_ranges, g->sm_count, g->s_side);
+    RSF_CUDA(cudaEventRecord(g->ev_prepass, g->s_side));
+  }
   RSF_CUDA(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
   if (int rc = snapshot_counters(g)) return rc;
   // K-class extension: the class planes are updated with the weights from BEFORE this frame's TSDF update
@@ -492,6 +503,8 @@ int rsf_create(const rsf_options* opts, rsf_grid_t* out) {
   ok = ok && cudaHostAlloc((void**)&g->h_ctr, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaHostAlloc((void**)&g->h_ctr_snap, sizeof(Counters), cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&g->ev_alloc_done, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->ev_prepass_go, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->ev_prepass, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&g->ev_snap, cudaEventDisableTiming) == cudaSuccess;
   if (ok) {
     // key = kEmptyKey (all ones), val = kValFree (-1)
@@ -551,6 +564,8 @@ int rsf_destroy(rsf_grid_t g) {
   if (g->h_ctr) cudaFreeHost(g->h_ctr);
   if (g->h_ctr_snap) cudaFreeHost(g->h_ctr_snap);
   if (g->ev_alloc_done) cudaEventDestroy(g->ev_alloc_done);
+  if (g->ev_prepass_go) cudaEventDestroy(g->ev_prepass_go);
+  if (g->ev_prepass) cudaEventDestroy(g->ev_prepass);
   if (g->ev_snap) cudaEventDestroy(g->ev_snap);
   for (auto& v : g->prof_events)
     for (auto& e : v) {
@@ -925,11 +940,13 @@ int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float* depth,
     if (rc_H != g->link.H || rc_W != g->link.W) return fail(RSF_ERR_INVALID, "raycast size differs from the linked planes");
   }
   DeviceGuard dg(g->device);
-  if (int rc = enqueue_integrate(g, f, rgb, depth, ht, lt)) return rc;
+  if (int rc = enqueue_integrate(g, f, rgb, depth, ht, lt, nullptr, false, 1.f, 1.f, nullptr, &rf)) return rc;
+  RSF_CUDA(cudaStreamWaitEvent(g->stream, g->ev_prepass, 0));      // tile ranges of `rf` (side stream, overlapped with integrate)
+  const int patch_rows = (rc_H + 3) / 4;
   if (world <= 1) {
     ProfScope p(g, RSF_PROF_RAYCAST);
-    launch_raycast(g->view, rf, g->opt.truncation / 2, g->d_ranges, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
-                   depth_out, prob_out, g->sm_count, g->stream);
+    launch_raycast_band(g->view, rf, g->opt.truncation / 2, g->d_ranges, reinterpret_cast<uchar4*>(rgba), reinterpret_cast<uchar4*>(normal),
+                        depth_out, prob_out, g->sm_count, g->stream, 0, patch_rows, 0);
     RSF_CUDA(cudaGetLastError());
     return RSF_OK;
   }
@@ -938,8 +955,8 @@ int rsf_shard_frame_device(rsf_grid_t g, const uint8_t* rgb, const float* depth,
   const int plane_spec = g->link.n_planes | (int)(g->link.skip_mask << 8);
   {
     ProfScope p(g, RSF_PROF_RAYCAST);
-    launch_raycast(g->view, rf, g->opt.truncation / 2, g->d_ranges, nullptr, nullptr, nullptr, nullptr, g->sm_count, g->stream,
-                   planes, plane_spec);
+    launch_raycast_band(g->view, rf, g->opt.truncation / 2, g->d_ranges, nullptr, nullptr, nullptr, nullptr, g->sm_count, g->stream,
+                        0, patch_rows, 0, planes, plane_spec);
   }
   launch_shard_signal(g->link.flags + rank, seq, g->stream);
   if (rank == g->link.root) {
